@@ -1,0 +1,275 @@
+"""ctypes loader for libsahbvh_b200.so -- the B200 closest-hit path of the SAH-BVH ray tracer.
+
+The product is the C/CUDA shared library (``csrc/``, C-ABI in ``include/sahbvh_gpu.h`` and the
+reference-named functions in ``include/sahbvh_ref_api.h``).  This module only binds it for the
+Python test / bench harness: numpy record dtypes that match the reference's struct layouts and
+thin wrappers with the same names and argument meaning as the C entry points.
+
+There is no CPU traversal here and no fallback: if the shared library is missing the import
+fails, and if no CUDA device is usable every trace call raises ``SahBvhError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsahbvh_b200.so")
+
+RAY_DT = np.dtype([("o", np.float32, 3), ("d", np.float32, 3)])                         # Ray, ray.h:5-8
+SPHERE_DT = np.dtype([("c", np.float32, 3), ("r", np.float32), ("rgba", np.uint8, 4)])   # Sphere, sphere.h:7-11
+HIT_DT = np.dtype([("t", np.float32), ("prim", np.int32), ("p", np.float32, 3), ("n", np.float32, 3)])  # gpu_hit
+CAMERA_DT = np.dtype([("position", np.float32, 3), ("forward", np.float32, 3), ("right", np.float32, 3),
+                      ("up", np.float32, 3), ("yaw", np.float32), ("pitch", np.float32),
+                      ("fov", np.float32), ("move", np.int32)])                          # Camera, camera.h:5-14
+
+EXPORTED_SYMBOLS = [
+    # include/sahbvh_gpu.h
+    "sahbvh_last_error", "sahbvh_device_count", "sahbvh_version", "sahbvh_kernel_launches",
+    "gpu_bvh_upload", "gpu_bvh_build", "gpu_bvh_free", "gpu_bvh_get_info",
+    "gpu_trace_closest_hit", "gpu_trace_closest_hit_dev", "gpu_trace_primary", "gpu_trace_primary_dev",
+    "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
+    # include/sahbvh_ref_api.h
+    "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
+    "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
+    "build_bvh_node", "free_bvh", "ray_sphere_intersect", "ray_aabb_intersect", "ray_bvh_intersect",
+    "get_camera_ray", "get_camera_ray_wh", "camera_update",
+    "random_float", "random_in_unit_sphere", "random_on_hemisphere",
+    "create_benchmark_sphere", "create_sphere", "create_random_sphere",
+    "sahbvh_fill_benchmark_scene", "sahbvh_fill_random_scene", "sahbvh_fill_benchmark_rays",
+    "sahbvh_default_camera", "sahbvh_fill_bounce_rays",
+]
+
+
+class SahBvhError(RuntimeError):
+    pass
+
+
+class BvhInfo(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_spheres", C.c_int32), ("n_inner", C.c_int32),
+                ("n_leaf_refs", C.c_int32), ("max_depth", C.c_int32), ("multi_leaves", C.c_int32),
+                ("empty_leaves", C.c_int32), ("reserved", C.c_int32), ("max_radius", C.c_float),
+                ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3), ("device_bytes", C.c_int64)]
+
+    def as_dict(self):
+        d = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+class TraceStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("inner_visits", C.c_uint64), ("sphere_tests", C.c_uint64),
+                ("exact_box_tests", C.c_uint64), ("hits", C.c_uint64), ("max_stack", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C cs201_sah-bvh_ray_tracer_b200`). There is no Python/CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.sahbvh_last_error.restype = C.c_char_p
+    lib.sahbvh_version.restype = C.c_char_p
+    lib.sahbvh_kernel_launches.restype = C.c_uint64
+    lib.build_bvh_node.restype = C.c_void_p
+    lib.free_bvh.restype = None
+    lib.gpu_bvh_free.restype = None
+    return lib
+
+
+lib = _load()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise SahBvhError(f"{what} failed ({rc}): {lib.sahbvh_last_error().decode()}")
+
+
+def device_count() -> int:
+    return int(lib.sahbvh_device_count())
+
+
+def kernel_launches() -> int:
+    return int(lib.sahbvh_kernel_launches())
+
+
+def default_camera() -> np.ndarray:
+    """main.c:203-211"""
+    cam = np.zeros(1, CAMERA_DT)
+    cam["position"] = (0, 4, 50)
+    cam["forward"] = (0, 0, -1)
+    cam["right"] = (1, 0, 0)
+    cam["up"] = (0, 1, 0)
+    cam["yaw"] = np.float32(-np.pi)
+    cam["fov"] = 45.0
+    return cam
+
+
+def srand(seed: int):
+    C.CDLL(None).srand(C.c_uint(seed))
+
+
+def benchmark_scene(n: int) -> np.ndarray:
+    """benchmark.c:306-314 through the library's create_benchmark_sphere (glibc rand() stream)."""
+    s = np.zeros(n + 1, SPHERE_DT)
+    lib.sahbvh_fill_benchmark_scene(C.c_int(n), _ptr(s))
+    return s
+
+
+def random_scene(n: int) -> np.ndarray:
+    """main.c:218-221 through the library's create_random_sphere."""
+    s = np.zeros(n + 1, SPHERE_DT)
+    lib.sahbvh_fill_random_scene(C.c_int(n), _ptr(s))
+    return s
+
+
+def benchmark_rays(n: int) -> np.ndarray:
+    """benchmark.c:232-240"""
+    r = np.zeros(n, RAY_DT)
+    lib.sahbvh_fill_benchmark_rays(C.c_int64(n), _ptr(r))
+    return r
+
+
+def bounce_rays(hits: np.ndarray) -> np.ndarray:
+    """renderer.c:51-54"""
+    hits = np.ascontiguousarray(hits)
+    out = np.zeros(len(hits), RAY_DT)
+    lib.sahbvh_fill_bounce_rays.restype = C.c_int64
+    m = lib.sahbvh_fill_bounce_rays(_ptr(hits), C.c_int64(len(hits)), _ptr(out))
+    return out[:m].copy()
+
+
+def build_bvh_node(spheres: np.ndarray, start: int, end: int, depth: int = 0) -> int:
+    """bvh.c:117 signature; returns the BVHNode* as an integer. Permutes ``spheres`` in place."""
+    root = lib.build_bvh_node(_ptr(spheres), C.c_int(start), C.c_int(end), C.c_int(depth))
+    if not root:
+        raise SahBvhError("build_bvh_node returned NULL")
+    return root
+
+
+def free_bvh(root: int):
+    lib.free_bvh(C.c_void_p(root))
+
+
+class GpuBvh:
+    """Owner of one ``gpu_bvh*`` (flattened tree + SoA spheres on one device)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def upload(cls, spheres: np.ndarray, n: int, root: int, device: int = -1) -> "GpuBvh":
+        h = C.c_void_p()
+        _check(lib.gpu_bvh_upload(_ptr(spheres), C.c_int(n), C.c_void_p(root), C.c_int(device), C.byref(h)),
+               "gpu_bvh_upload")
+        return cls(h)
+
+    @classmethod
+    def build(cls, spheres: np.ndarray, n_total: int, start: int, end: int, depth: int = 0, device: int = -1) -> "GpuBvh":
+        h = C.c_void_p()
+        _check(lib.gpu_bvh_build(_ptr(spheres), C.c_int(n_total), C.c_int(start), C.c_int(end), C.c_int(depth),
+                                 C.c_int(device), C.byref(h)), "gpu_bvh_build")
+        return cls(h)
+
+    def close(self):
+        if self._h:
+            lib.gpu_bvh_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        i = BvhInfo()
+        _check(lib.gpu_bvh_get_info(self._h, C.byref(i)), "gpu_bvh_get_info")
+        return i.as_dict()
+
+    # ---- host-buffer entry points (H2D + kernel + D2H inside the call) ----
+    def trace_closest_hit(self, rays: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == RAY_DT
+        if out is None:
+            out = np.empty(len(rays), HIT_DT)
+        _check(lib.gpu_trace_closest_hit(self._h, _ptr(rays), C.c_int64(len(rays)), _ptr(out)), "gpu_trace_closest_hit")
+        return out
+
+    def trace_closest_hit_ptr(self, rays_ptr: int, n: int, out_ptr: int):
+        _check(lib.gpu_trace_closest_hit(self._h, C.c_void_p(rays_ptr), C.c_int64(n), C.c_void_p(out_ptr)),
+               "gpu_trace_closest_hit")
+
+    def trace_primary(self, cam: np.ndarray, width: int, height: int, y0: int = 0, y1: int | None = None,
+                      out: np.ndarray | None = None) -> np.ndarray:
+        y1 = height if y1 is None else y1
+        if out is None:
+            out = np.empty((y1 - y0) * width, HIT_DT)
+        _check(lib.gpu_trace_primary(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                     _ptr(out)), "gpu_trace_primary")
+        return out
+
+    def trace_primary_ptr(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, out_ptr: int):
+        _check(lib.gpu_trace_primary(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                     C.c_void_p(out_ptr)), "gpu_trace_primary")
+
+    def trace_brute_force(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays)
+        out = np.empty(len(rays), HIT_DT)
+        _check(lib.gpu_trace_brute_force(self._h, _ptr(rays), C.c_int64(len(rays)), _ptr(out)), "gpu_trace_brute_force")
+        return out
+
+    # ---- device-pointer entry points (asynchronous on `stream`) ----
+    def trace_closest_hit_dev(self, d_rays: int, n: int, d_out: int, stream: int = 0):
+        _check(lib.gpu_trace_closest_hit_dev(self._h, C.c_void_p(d_rays), C.c_int64(n), C.c_void_p(d_out),
+                                             C.c_void_p(stream)), "gpu_trace_closest_hit_dev")
+
+    def trace_primary_dev(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_out: int, stream: int = 0):
+        _check(lib.gpu_trace_primary_dev(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                         C.c_void_p(d_out), C.c_void_p(stream)), "gpu_trace_primary_dev")
+
+    def trace_closest_hit_stats(self, d_rays: int, n: int, d_out: int) -> dict:
+        st = TraceStats()
+        _check(lib.gpu_trace_closest_hit_stats(self._h, C.c_void_p(d_rays), C.c_int64(n), C.c_void_p(d_out), C.byref(st)),
+               "gpu_trace_closest_hit_stats")
+        return st.as_dict()
+
+    def trace_primary_stats(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_out: int) -> dict:
+        st = TraceStats()
+        _check(lib.gpu_trace_primary_stats(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                           C.c_void_p(d_out), C.byref(st)), "gpu_trace_primary_stats")
+        return st.as_dict()
+
+
+def generate_primary_rays(cam: np.ndarray, width: int, height: int, y0: int = 0, y1: int | None = None,
+                          device: int = -1) -> np.ndarray:
+    y1 = height if y1 is None else y1
+    out = np.empty((y1 - y0) * width, RAY_DT)
+    _check(lib.gpu_generate_primary_rays(_ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                         _ptr(out), C.c_int(device)), "gpu_generate_primary_rays")
+    return out
+
+
+# ---- ray / row sharding across ranks: contiguous, no data-path collective ----
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous ray range [lo, hi) of rank ``rank`` out of ``world`` (sizes differ by at most 1)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def shard_rows(height: int, rank: int, world: int, align: int = 8) -> tuple[int, int]:
+    """Row band [y0, y1) of a frame; bands are multiples of ``align`` rows (the kernel's CTA tile
+    height) except possibly the last, so no CTA straddles two ranks."""
+    blocks = (height + align - 1) // align
+    b0, b1 = blocks * rank // world, blocks * (rank + 1) // world
+    return min(b0 * align, height), min(b1 * align, height)

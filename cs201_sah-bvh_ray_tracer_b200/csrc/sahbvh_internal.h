@@ -1,0 +1,70 @@
+/* sahbvh_internal.h -- shared between the host C sources and the CUDA translation unit. */
+#ifndef SAHBVH_INTERNAL_H
+#define SAHBVH_INTERNAL_H
+
+#include "sahbvh_gpu.h"
+#include "sahbvh_ref_api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Intermediate array tree, preorder (root = 0).  One entry per reference BVHNode. */
+typedef struct sah_node {
+    float lo[3], hi[3]; /* node->bounds (bvh.c:120-125) */
+    int32_t left, right; /* preorder ids; -1 on leaves */
+    int32_t sphere;      /* leaf: index of spheres[start] -- the only sphere hit.c:98-99 tests; -1 on inner */
+    int32_t count;       /* leaf: sphere_count */
+} sah_node;
+
+typedef struct sah_tree {
+    sah_node *nodes;
+    int64_t used, cap;
+} sah_tree;
+
+/* Flattened, device-ready form.
+ *
+ * Inner node = 64 bytes = 4 x 16-byte words, 64-byte aligned:
+ *   w0 = { L.lo.x, L.lo.y, L.lo.z, L.hi.x }
+ *   w1 = { L.hi.y, L.hi.z, R.lo.x, R.lo.y }
+ *   w2 = { R.lo.z, R.hi.x, R.hi.y, R.hi.z }
+ *   w3 = { left_ref, right_ref, 0, 0 }              (int32)
+ * child ref >= 0 : index of another inner node;  ref < 0 : leaf, sphere index = ~ref.
+ * A leaf's inline box is the reference leaf's node->bounds, except for sphere_count==0
+ * leaves (inverted-infinite bounds) which carry the PARENT's bounds: the reference
+ * reaches such a leaf iff the parent's own box test passed, and its own box always passes.
+ * Sphere index == n_spheres encodes the reference's one-past-the-end read (never hit);
+ * SAHBVH_REF_NONE marks the absent sibling of a synthetic root (tree that is a single leaf).
+ */
+#define SAHBVH_REF_NONE ((int32_t)0x80000000)
+#define SAHBVH_STACK_MAX 64
+
+typedef struct flat_bvh {
+    float *nodes;     /* n_inner * 16 floats (w3 holds int32 bit patterns) */
+    float *spheres4;  /* (n_spheres + 1) * 4 : cx, cy, cz, r ; entry n is a NaN sentinel */
+    uint32_t *colors; /* n_spheres RGBA8 (kept for the shading row that comes next) */
+    gpu_bvh_info info;
+} flat_bvh;
+
+void sahbvh_set_error(const char *fmt, ...);
+
+/* sah_builder.c */
+int sah_tree_init(sah_tree *t, int64_t cap);
+void sah_tree_free(sah_tree *t);
+int sah_build(sah_tree *t, Sphere *spheres, int start, int end, int depth);
+BVHNode *sah_tree_to_pointers(const sah_tree *t, Sphere *spheres);
+
+/* flatten.c */
+int sah_tree_from_pointers(sah_tree *t, const BVHNode *root, const Sphere *base, int n);
+int flat_bvh_from_tree(flat_bvh *f, const sah_tree *t, const Sphere *spheres, int n);
+void flat_bvh_release(flat_bvh *f);
+
+/* gpu_api.cu */
+int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out);
+int sahbvh_scalar_trace(const BVHNode *root, const Ray *ray, HitRecord *out); /* ray_bvh_intersect backend */
+void sahbvh_scalar_forget(const BVHNode *root);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,719 @@
+/*
+ * sahbvh_kernels.cu -- sm_100a kernels + the C-ABI of include/sahbvh_gpu.h.
+ *
+ *   K1 k_trace_rays     ray buffer -> hit buffer        replaces the loop benchmark.c:230-245 /
+ *                                                       renderer.c:29-32 over ray_bvh_intersect (hit.c:91)
+ *   K2 k_trace_primary  fused camera rays + closest hit replaces main.c:356-366 (get_camera_ray ray.c:17 +
+ *                                                       the BVH branch of trace_ray renderer.c:29-32)
+ *   K2' k_primary_rays  ray generation only             parity aid for ray.c:17-32
+ *   K3 k_brute_force    all-spheres closest hit         renderer.c:33-44 (ties -> lowest index)
+ *
+ * FP32 CUDA-core work (box slabs, sphere quadratics); tensor cores are not applicable.
+ * Built with -fmad=false; the parity-critical arithmetic additionally uses explicit _rn
+ * intrinsics (traverse_core.cuh), the conservative interior test uses explicit FMAs.
+ */
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "sahbvh_internal.h"
+#include "traverse_core.cuh"
+
+static_assert(sizeof(SahHit) == sizeof(gpu_hit), "hit record");
+static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
+
+#define TRACE_THREADS 128
+#define PRIMARY_THREADS 256 /* 32 x 8 pixels per CTA, one 8x4 tile per warp */
+
+static std::atomic<unsigned long long> g_launches{0};
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            sahbvh_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SAHBVH_E_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+/* ------------------------------------------------------------------------------------------ */
+/* kernels                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ void store_hit(gpu_hit *out, const SahHit &h)
+{
+    float4 a = make_float4(h.t, __int_as_float(h.prim), h.px, h.py);
+    float4 b = make_float4(h.pz, h.nx, h.ny, h.nz);
+    float4 *o = reinterpret_cast<float4 *>(out);
+    o[0] = a;
+    o[1] = b;
+}
+
+__device__ __forceinline__ void flush_counters(const SahCounters &c, unsigned long long hit, unsigned long long *g)
+{
+    unsigned long long v[4] = {c.inner, c.spheres, c.exact, hit};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&g[k], x);
+    }
+    unsigned long long m = c.max_stack;
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long y = __shfl_xor_sync(0xffffffffu, m, o);
+        m = y > m ? y : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(&g[4], m);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4, int n_spheres, float r_max,
+             const float *__restrict__ rays, long long n, gpu_hit *__restrict__ out, unsigned long long *counters)
+{
+    int32_t stack[SAH_STACK_MAX];
+    SahCounters cnt = {0, 0, 0, 0};
+    unsigned long long hits = 0;
+    const long long stride = (long long)gridDim.x * TRACE_THREADS;
+    for (long long i = (long long)blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += stride) {
+        const float *rp = rays + i * 6;
+        SahRay r;
+        sah_ray_setup(r, __ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3), __ldg(rp + 4), __ldg(rp + 5), r_max);
+        SahHit h;
+        sah_trace_one<COUNT>(nodes, spheres4, n_spheres, r, stack, 1, h, &cnt);
+        store_hit(out + i, h);
+        if (COUNT) hits += (h.prim >= 0);
+    }
+    if (COUNT) flush_counters(cnt, hits, counters);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PRIMARY_THREADS)
+k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spheres4, int n_spheres, float r_max,
+                SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, unsigned long long *counters)
+{
+    int32_t stack[SAH_STACK_MAX];
+    SahCounters cnt = {0, 0, 0, 0};
+    unsigned long long hits = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int y = y0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (x < width && y < y1) {
+        float dx, dy, dz;
+        sah_primary_dir(cam, x, y, dx, dy, dz);
+        SahRay r;
+        sah_ray_setup(r, cam.px, cam.py, cam.pz, dx, dy, dz, r_max);
+        SahHit h;
+        sah_trace_one<COUNT>(nodes, spheres4, n_spheres, r, stack, 1, h, &cnt);
+        store_hit(out + (size_t)(y - y0) * (size_t)width + (size_t)x, h);
+        if (COUNT) hits += (h.prim >= 0);
+    }
+    if (COUNT) flush_counters(cnt, hits, counters);
+}
+
+__global__ void __launch_bounds__(PRIMARY_THREADS)
+k_primary_rays(SahCamera cam, int width, int y0, int y1, float *__restrict__ out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int y = y0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (x < width && y < y1) {
+        float dx, dy, dz;
+        sah_primary_dir(cam, x, y, dx, dy, dz);
+        float *o = out + ((size_t)(y - y0) * (size_t)width + (size_t)x) * 6;
+        o[0] = cam.px; o[1] = cam.py; o[2] = cam.pz;
+        o[3] = dx; o[4] = dy; o[5] = dz;
+    }
+}
+
+/* renderer.c:33-44: closest over ALL spheres, strict < so the lowest index wins ties */
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_brute_force(const float *__restrict__ spheres4, int n_spheres, const float *__restrict__ rays, long long n,
+              gpu_hit *__restrict__ out)
+{
+    __shared__ float4 tile[TRACE_THREADS];
+    long long i = (long long)blockIdx.x * TRACE_THREADS + threadIdx.x;
+    bool live = i < n;
+    SahRay r;
+    if (live) {
+        const float *rp = rays + i * 6;
+        sah_ray_setup(r, rp[0], rp[1], rp[2], rp[3], rp[4], rp[5], 0.0f);
+    } else {
+        sah_ray_setup(r, 0, 0, 0, 0, 0, 0, 0.0f);
+    }
+    float best_t = INFINITY;
+    int best = -1;
+    for (int base = 0; base < n_spheres; base += TRACE_THREADS) {
+        int j = base + threadIdx.x;
+        tile[threadIdx.x] = j < n_spheres ? reinterpret_cast<const float4 *>(spheres4)[j]
+                                          : make_float4(0, 0, 0, __int_as_float(0x7fffffff));
+        __syncthreads();
+        int m = min(TRACE_THREADS, n_spheres - base);
+        if (live) {
+            for (int k = 0; k < m; k++) {
+                float4 s = tile[k];
+                float t;
+                if (sah_sphere_t(r, s.x, s.y, s.z, s.w, t) && t < best_t) { best_t = t; best = base + k; }
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        SahHit h;
+        if (best >= 0) {
+            float4 s = reinterpret_cast<const float4 *>(spheres4)[best];
+            sah_finish_hit(r, best_t, best, s.x, s.y, s.z, h);
+        } else {
+            sah_miss(h);
+        }
+        store_hit(out + i, h);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* handle                                                                                       */
+/* ------------------------------------------------------------------------------------------ */
+
+struct gpu_bvh {
+    int device;
+    float *d_nodes;
+    float *d_spheres4;
+    uint32_t *d_colors;
+    unsigned long long *d_counters;
+    gpu_bvh_info info;
+    cudaStream_t streams[2];
+    /* staging for the host-buffer entry points (grown on demand) */
+    void *d_in[2];
+    void *d_out[2];
+    size_t in_cap, out_cap;
+    int sm_count;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (dev != prev && cudaSetDevice(dev) != cudaSuccess) return;
+        ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+extern "C" int sahbvh_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" uint64_t sahbvh_kernel_launches(void) { return (uint64_t)g_launches.load(); }
+
+extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
+{
+    if (!f || !out) {
+        sahbvh_set_error("gpu_bvh_from_flat: NULL argument");
+        return SAHBVH_E_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        sahbvh_set_error("no usable CUDA device (%s); this library has no CPU traversal path",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return SAHBVH_E_CUDA;
+    }
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    if (device >= ndev) {
+        sahbvh_set_error("device %d out of range (%d devices)", device, ndev);
+        return SAHBVH_E_ARG;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        sahbvh_set_error("cudaSetDevice(%d) failed", device);
+        return SAHBVH_E_CUDA;
+    }
+    gpu_bvh *b = (gpu_bvh *)calloc(1, sizeof(gpu_bvh));
+    if (!b) return SAHBVH_E_NOMEM;
+    b->device = device;
+    b->info = f->info;
+    b->info.device = device;
+    size_t node_bytes = (size_t)f->info.n_inner * 64;
+    size_t sph_bytes = ((size_t)f->info.n_spheres + 1) * 16;
+    size_t col_bytes = ((size_t)f->info.n_spheres + 1) * 4;
+    cudaError_t err = cudaSuccess;
+    do {
+        if ((err = cudaMalloc(&b->d_nodes, node_bytes)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&b->d_spheres4, sph_bytes)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&b->d_colors, col_bytes)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&b->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) break;
+        if ((err = cudaMemcpy(b->d_nodes, f->nodes, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(b->d_spheres4, f->spheres4, sph_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(b->d_colors, f->colors, col_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((err = cudaStreamCreateWithFlags(&b->streams[0], cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((err = cudaStreamCreateWithFlags(&b->streams[1], cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((err = cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) break;
+    } while (0);
+    if (err != cudaSuccess) {
+        sahbvh_set_error("gpu_bvh upload failed: %s", cudaGetErrorString(err));
+        gpu_bvh_free(b);
+        return SAHBVH_E_CUDA;
+    }
+    b->info.device_bytes = (int64_t)(node_bytes + sph_bytes + col_bytes);
+    *out = b;
+    return SAHBVH_OK;
+}
+
+extern "C" int gpu_bvh_upload(const Sphere *permuted, int n, const BVHNode *root, int device, gpu_bvh **out)
+{
+    if (!out) {
+        sahbvh_set_error("gpu_bvh_upload: NULL out");
+        return SAHBVH_E_ARG;
+    }
+    *out = nullptr;
+    sah_tree t;
+    int rc = sah_tree_init(&t, 2 * (int64_t)(n > 0 ? n : 1) + 16);
+    if (rc != SAHBVH_OK) return rc;
+    rc = sah_tree_from_pointers(&t, root, permuted, n);
+    flat_bvh f;
+    memset(&f, 0, sizeof f);
+    if (rc == SAHBVH_OK) rc = flat_bvh_from_tree(&f, &t, permuted, n);
+    if (rc == SAHBVH_OK) rc = gpu_bvh_from_flat(&f, device, out);
+    flat_bvh_release(&f);
+    sah_tree_free(&t);
+    return rc;
+}
+
+extern "C" int gpu_bvh_build(Sphere *spheres, int n_total, int start, int end, int depth, int device, gpu_bvh **out)
+{
+    if (!out || !spheres || start < 0 || end < start || end > n_total) {
+        sahbvh_set_error("gpu_bvh_build: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    *out = nullptr;
+    sah_tree t;
+    int rc = sah_tree_init(&t, 2 * (int64_t)(end - start + 1) + 16);
+    if (rc != SAHBVH_OK) return rc;
+    rc = sah_build(&t, spheres, start, end, depth);
+    flat_bvh f;
+    memset(&f, 0, sizeof f);
+    if (rc == SAHBVH_OK) rc = flat_bvh_from_tree(&f, &t, spheres, n_total);
+    if (rc == SAHBVH_OK) rc = gpu_bvh_from_flat(&f, device, out);
+    flat_bvh_release(&f);
+    sah_tree_free(&t);
+    return rc;
+}
+
+extern "C" void gpu_bvh_free(gpu_bvh *b)
+{
+    if (!b) return;
+    DeviceGuard guard(b->device);
+    for (int k = 0; k < 2; k++) {
+        if (b->streams[k]) cudaStreamDestroy(b->streams[k]);
+        if (b->d_in[k]) cudaFree(b->d_in[k]);
+        if (b->d_out[k]) cudaFree(b->d_out[k]);
+    }
+    if (b->d_nodes) cudaFree(b->d_nodes);
+    if (b->d_spheres4) cudaFree(b->d_spheres4);
+    if (b->d_colors) cudaFree(b->d_colors);
+    if (b->d_counters) cudaFree(b->d_counters);
+    free(b);
+}
+
+extern "C" int gpu_bvh_get_info(const gpu_bvh *b, gpu_bvh_info *info)
+{
+    if (!b || !info) {
+        sahbvh_set_error("gpu_bvh_get_info: NULL argument");
+        return SAHBVH_E_ARG;
+    }
+    *info = b->info;
+    return SAHBVH_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* launches                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+
+static int trace_grid(const gpu_bvh *b, long long n)
+{
+    long long blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;
+    long long cap = (long long)b->sm_count * 64; /* grid-stride beyond that */
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+static int launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count)
+{
+    if (n == 0) return SAHBVH_OK;
+    int grid = trace_grid(b, n);
+    if (count)
+        k_trace_rays<true><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+                                                          (const float *)d_rays, n, (gpu_hit *)d_out, b->d_counters);
+    else
+        k_trace_rays<false><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+                                                           (const float *)d_rays, n, (gpu_hit *)d_out, nullptr);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return SAHBVH_OK;
+}
+
+static void make_camera(const Camera *cam, int width, int height, SahCamera *c)
+{
+    /* ray.c:18-24, evaluated once per frame on the host with the reference's double/float mix */
+    Camera tmp = *cam;
+    float aspect = (float)width / (float)height;
+    float fov_rad = (float)((double)tmp.fov * (M_PI / (double)180.0f));
+    float half_h = (float)tan((double)(fov_rad / 2.0f));
+    float half_w = aspect * half_h;
+    Vec3 horizontal = vec3_multiply(tmp.right, 2.0f * half_w);
+    Vec3 vertical = vec3_multiply(tmp.up, 2.0f * half_h);
+    c->px = tmp.position.x; c->py = tmp.position.y; c->pz = tmp.position.z;
+    c->fx = tmp.forward.x; c->fy = tmp.forward.y; c->fz = tmp.forward.z;
+    c->hx = horizontal.x; c->hy = horizontal.y; c->hz = horizontal.z;
+    c->vx = vertical.x; c->vy = vertical.y; c->vz = vertical.z;
+    c->aspect = aspect;
+    c->fw = (float)width;
+    c->fh = (float)height;
+}
+
+static int launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
+                          cudaStream_t st, bool count)
+{
+    if (y1 <= y0 || width <= 0) return SAHBVH_OK;
+    SahCamera c;
+    make_camera(cam, width, height, &c);
+    dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
+    if (count)
+        k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+                                                               c, width, y0, y1, (gpu_hit *)d_out, b->d_counters);
+    else
+        k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+                                                                c, width, y0, y1, (gpu_hit *)d_out, nullptr);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return SAHBVH_OK;
+}
+
+static int check_frame(const gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, const void *out)
+{
+    if (!b || !cam || !out || width <= 0 || height <= 0 || y0 < 0 || y1 < y0 || y1 > height) {
+        sahbvh_set_error("bad frame arguments (width=%d height=%d rows=[%d,%d))", width, height, y0, y1);
+        return SAHBVH_E_ARG;
+    }
+    return SAHBVH_OK;
+}
+
+static int ensure_staging(gpu_bvh *b, size_t in_bytes, size_t out_bytes)
+{
+    if (in_bytes > b->in_cap) {
+        for (int k = 0; k < 2; k++) {
+            if (b->d_in[k]) cudaFree(b->d_in[k]);
+            b->d_in[k] = nullptr;
+        }
+        b->in_cap = 0;
+        for (int k = 0; k < 2; k++) CU_TRY(cudaMalloc(&b->d_in[k], in_bytes));
+        b->in_cap = in_bytes;
+    }
+    if (out_bytes > b->out_cap) {
+        for (int k = 0; k < 2; k++) {
+            if (b->d_out[k]) cudaFree(b->d_out[k]);
+            b->d_out[k] = nullptr;
+        }
+        b->out_cap = 0;
+        for (int k = 0; k < 2; k++) CU_TRY(cudaMalloc(&b->d_out[k], out_bytes));
+        b->out_cap = out_bytes;
+    }
+    return SAHBVH_OK;
+}
+
+#define HOST_CHUNK_RAYS (1ll << 21) /* 2 Mi rays: 48 MiB in, 64 MiB out per chunk */
+
+extern "C" int gpu_trace_closest_hit_dev(gpu_bvh *b, const void *d_rays, int64_t n, void *d_out, void *stream)
+{
+    if (!b || n < 0 || (n > 0 && (!d_rays || !d_out))) {
+        sahbvh_set_error("gpu_trace_closest_hit_dev: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    DeviceGuard guard(b->device);
+    return launch_rays(b, d_rays, n, d_out, (cudaStream_t)stream, false);
+}
+
+extern "C" int gpu_trace_closest_hit(gpu_bvh *b, const Ray *rays, int64_t n, gpu_hit *out)
+{
+    if (!b || n < 0 || (n > 0 && (!rays || !out))) {
+        sahbvh_set_error("gpu_trace_closest_hit: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    if (n == 0) return SAHBVH_OK;
+    DeviceGuard guard(b->device);
+    long long chunk = n < HOST_CHUNK_RAYS ? n : HOST_CHUNK_RAYS;
+    int rc = ensure_staging(b, (size_t)chunk * sizeof(Ray), (size_t)chunk * sizeof(gpu_hit));
+    if (rc != SAHBVH_OK) return rc;
+    int k = 0;
+    for (long long off = 0; off < n; off += chunk, k ^= 1) {
+        long long m = n - off < chunk ? n - off : chunk;
+        cudaStream_t st = b->streams[k];
+        CU_TRY(cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
+        rc = launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
+        if (rc != SAHBVH_OK) return rc;
+        CU_TRY(cudaMemcpyAsync(out + off, b->d_out[k], (size_t)m * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
+        /* the staging pair k is reused two chunks later: the stream orders it */
+    }
+    CU_TRY(cudaStreamSynchronize(b->streams[0]));
+    CU_TRY(cudaStreamSynchronize(b->streams[1]));
+    return SAHBVH_OK;
+}
+
+extern "C" int gpu_trace_primary_dev(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
+                                     void *d_out, void *stream)
+{
+    int rc = check_frame(b, cam, width, height, y0, y1, d_out);
+    if (rc != SAHBVH_OK) return rc;
+    DeviceGuard guard(b->device);
+    return launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false);
+}
+
+extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out)
+{
+    int rc = check_frame(b, cam, width, height, y0, y1, out);
+    if (rc != SAHBVH_OK) return rc;
+    if (y1 == y0) return SAHBVH_OK;
+    DeviceGuard guard(b->device);
+    /* row bands of ~2 Mi pixels so the D2H copy of one band overlaps the next band's kernel */
+    int band = (int)(HOST_CHUNK_RAYS / width);
+    band = band < 8 ? 8 : (band / 8) * 8;
+    if (band > y1 - y0) band = ((y1 - y0 + 7) / 8) * 8;
+    rc = ensure_staging(b, 0, (size_t)band * (size_t)width * sizeof(gpu_hit));
+    if (rc != SAHBVH_OK) return rc;
+    int k = 0;
+    for (int ya = y0; ya < y1; ya += band, k ^= 1) {
+        int yb = ya + band < y1 ? ya + band : y1;
+        cudaStream_t st = b->streams[k];
+        rc = launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false);
+        if (rc != SAHBVH_OK) return rc;
+        CU_TRY(cudaMemcpyAsync(out + (size_t)(ya - y0) * (size_t)width, b->d_out[k],
+                               (size_t)(yb - ya) * (size_t)width * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(b->streams[0]));
+    CU_TRY(cudaStreamSynchronize(b->streams[1]));
+    return SAHBVH_OK;
+}
+
+extern "C" int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out, int device)
+{
+    if (!cam || !out || width <= 0 || height <= 0 || y0 < 0 || y1 < y0 || y1 > height) {
+        sahbvh_set_error("gpu_generate_primary_rays: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    if (y1 == y0) return SAHBVH_OK;
+    int ndev = sahbvh_device_count();
+    if (ndev == 0) {
+        sahbvh_set_error("no usable CUDA device");
+        return SAHBVH_E_CUDA;
+    }
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    SahCamera c;
+    make_camera(cam, width, height, &c);
+    size_t bytes = (size_t)(y1 - y0) * (size_t)width * sizeof(Ray);
+    float *d = nullptr;
+    CU_TRY(cudaMalloc(&d, bytes));
+    dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
+    k_primary_rays<<<grid, PRIMARY_THREADS>>>(c, width, y0, y1, d);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        sahbvh_set_error("gpu_generate_primary_rays: %s", cudaGetErrorString(e));
+        return SAHBVH_E_CUDA;
+    }
+    return SAHBVH_OK;
+}
+
+extern "C" int gpu_trace_brute_force(gpu_bvh *b, const Ray *rays, int64_t n, gpu_hit *out)
+{
+    if (!b || n < 0 || (n > 0 && (!rays || !out))) {
+        sahbvh_set_error("gpu_trace_brute_force: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    if (n == 0) return SAHBVH_OK;
+    DeviceGuard guard(b->device);
+    int rc = ensure_staging(b, (size_t)n * sizeof(Ray), (size_t)n * sizeof(gpu_hit));
+    if (rc != SAHBVH_OK) return rc;
+    cudaStream_t st = b->streams[0];
+    CU_TRY(cudaMemcpyAsync(b->d_in[0], rays, (size_t)n * sizeof(Ray), cudaMemcpyHostToDevice, st));
+    int grid = (int)((n + TRACE_THREADS - 1) / TRACE_THREADS);
+    k_brute_force<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, b->info.n_spheres, (const float *)b->d_in[0], n,
+                                                 (gpu_hit *)b->d_out[0]);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, b->d_out[0], (size_t)n * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SAHBVH_OK;
+}
+
+static int read_counters(gpu_bvh *b, uint64_t rays, gpu_trace_stats *stats)
+{
+    unsigned long long h[8];
+    CU_TRY(cudaMemcpy(h, b->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    stats->rays = rays;
+    stats->inner_visits = h[0];
+    stats->sphere_tests = h[1];
+    stats->exact_box_tests = h[2];
+    stats->hits = h[3];
+    stats->max_stack = h[4];
+    return SAHBVH_OK;
+}
+
+extern "C" int gpu_trace_closest_hit_stats(gpu_bvh *b, const void *d_rays, int64_t n, void *d_out, gpu_trace_stats *stats)
+{
+    if (!b || !stats || n < 0 || (n > 0 && (!d_rays || !d_out))) {
+        sahbvh_set_error("gpu_trace_closest_hit_stats: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    DeviceGuard guard(b->device);
+    CU_TRY(cudaMemset(b->d_counters, 0, 8 * sizeof(unsigned long long)));
+    int rc = launch_rays(b, d_rays, n, d_out, 0, true);
+    if (rc != SAHBVH_OK) return rc;
+    CU_TRY(cudaDeviceSynchronize());
+    return read_counters(b, (uint64_t)n, stats);
+}
+
+extern "C" int gpu_trace_primary_stats(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
+                                       void *d_out, gpu_trace_stats *stats)
+{
+    int rc = check_frame(b, cam, width, height, y0, y1, d_out);
+    if (rc != SAHBVH_OK) return rc;
+    if (!stats) return SAHBVH_E_ARG;
+    DeviceGuard guard(b->device);
+    CU_TRY(cudaMemset(b->d_counters, 0, 8 * sizeof(unsigned long long)));
+    rc = launch_primary(b, cam, width, height, y0, y1, d_out, 0, true);
+    if (rc != SAHBVH_OK) return rc;
+    CU_TRY(cudaDeviceSynchronize());
+    return read_counters(b, (uint64_t)(y1 - y0) * (uint64_t)width, stats);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* scalar drop-in backend: ray_bvh_intersect(Ray, BVHNode*) (hit.c:91)                          */
+/* ------------------------------------------------------------------------------------------ */
+
+struct ScalarEntry {
+    const BVHNode *root;
+    const Sphere *base;
+    gpu_bvh *bvh;
+};
+static std::mutex g_scalar_mu;
+static std::vector<ScalarEntry> g_scalar;
+
+/* The scalar signature does not carry the sphere array; recover [base, base+n) from the leaves. */
+static int scalar_span(const BVHNode *root, const Sphere **base, int *n)
+{
+    const Sphere *lo = nullptr, *hi = nullptr, *lo_any = nullptr;
+    std::vector<const BVHNode *> stk;
+    stk.push_back(root);
+    while (!stk.empty()) {
+        const BVHNode *p = stk.back();
+        stk.pop_back();
+        if (p->sphere) {
+            if (!lo_any || p->sphere < lo_any) lo_any = p->sphere;
+            if (p->sphere_count > 0) {
+                if (!lo || p->sphere < lo) lo = p->sphere;
+                const Sphere *last = p->sphere + (p->sphere_count - 1);
+                if (!hi || last > hi) hi = last;
+            }
+            continue;
+        }
+        if (!p->left || !p->right) {
+            sahbvh_set_error("ray_bvh_intersect: inner node with a NULL child");
+            return SAHBVH_E_ARG;
+        }
+        stk.push_back(p->left);
+        stk.push_back(p->right);
+    }
+    if (!lo) { /* no sphere at all: every leaf is empty */
+        *base = lo_any;
+        *n = 0;
+        return SAHBVH_OK;
+    }
+    if (lo_any < lo) lo = lo_any;
+    *base = lo;
+    *n = (int)(hi - lo) + 1;
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_scalar_trace(const BVHNode *root, const Ray *ray, HitRecord *out)
+{
+    if (!root || !ray || !out) {
+        sahbvh_set_error("ray_bvh_intersect: NULL argument");
+        return SAHBVH_E_ARG;
+    }
+    std::lock_guard<std::mutex> lock(g_scalar_mu);
+    ScalarEntry *e = nullptr;
+    for (auto &s : g_scalar)
+        if (s.root == root) e = &s;
+    if (!e) {
+        const Sphere *base = nullptr;
+        int n = 0;
+        int rc = scalar_span(root, &base, &n);
+        if (rc != SAHBVH_OK) return rc;
+        /* leaves that point past the recovered span (empty leaves at the array end, Q3) are
+         * clamped to the one-past-the-end sentinel by the flattener's index check below */
+        sah_tree t;
+        rc = sah_tree_init(&t, 2 * (int64_t)(n > 0 ? n : 1) + 16);
+        if (rc != SAHBVH_OK) return rc;
+        rc = sah_tree_from_pointers(&t, root, base, 0x7ffffff0);
+        if (rc == SAHBVH_OK) {
+            for (int64_t i = 0; i < t.used; i++)
+                if (t.nodes[i].sphere > n) t.nodes[i].sphere = n;
+        }
+        flat_bvh f;
+        memset(&f, 0, sizeof f);
+        gpu_bvh *bvh = nullptr;
+        if (rc == SAHBVH_OK) rc = flat_bvh_from_tree(&f, &t, base, n);
+        if (rc == SAHBVH_OK) rc = gpu_bvh_from_flat(&f, -1, &bvh);
+        flat_bvh_release(&f);
+        sah_tree_free(&t);
+        if (rc != SAHBVH_OK) return rc;
+        g_scalar.push_back({root, base, bvh});
+        e = &g_scalar.back();
+    }
+    gpu_hit h;
+    int rc = gpu_trace_closest_hit(e->bvh, ray, 1, &h);
+    if (rc != SAHBVH_OK) return rc;
+    memset(out, 0, sizeof *out);
+    if (h.prim >= 0) {
+        out->t = h.t;
+        out->point.x = h.px; out->point.y = h.py; out->point.z = h.pz;
+        out->normal.x = h.nx; out->normal.y = h.ny; out->normal.z = h.nz;
+        out->hit_something = 1;
+        out->object = const_cast<Sphere *>(e->base) + h.prim;
+    }
+    return SAHBVH_OK;
+}
+
+extern "C" void sahbvh_scalar_forget(const BVHNode *root)
+{
+    std::lock_guard<std::mutex> lock(g_scalar_mu);
+    for (size_t i = 0; i < g_scalar.size(); i++) {
+        if (g_scalar[i].root == root) {
+            gpu_bvh_free(g_scalar[i].bvh);
+            g_scalar.erase(g_scalar.begin() + (long)i);
+            return;
+        }
+    }
+}

@@ -1,0 +1,302 @@
+/*
+ * traverse_core.cuh -- per-ray closest-hit arithmetic shared by every kernel in sahbvh_kernels.cu.
+ *
+ * Result contract (what makes the output identical to the reference):
+ *   hit(ray) = best over all LEAVES whose reference box test passes (hit.c:49-82, true
+ *   divisions, d==0 axis accepts everything) and whose reference sphere test passes
+ *   (hit.c:19-39: float disc, DOUBLE t, t > EPSILON), best = smaller t, equal t -> larger
+ *   post-build sphere index (hit.c:108 applied inductively, Q1).
+ * Interior boxes only cull (a leaf's exact test passing implies every ancestor's passes, Q7),
+ * so inner nodes use a cheaper CONSERVATIVE slab test:
+ *
+ *   t = fma(plane, inv_d, -o*inv_d)                     1 FFMA per plane
+ *   |t - t_ref| <= 4u|t_ref| + u|o*inv_d|               (u = 2^-24; the product plane*inv_d is
+ *                                                        exact inside the FMA, only o*inv_d and
+ *                                                        inv_d itself are rounded)
+ *   pass  <=>  max(tnear, 0) <= min(tfar*(1+2^-20) + A2, best_s)
+ *   A2     =  2^-20 * max_axis |o*inv_d|                 (>= 4x the bound, both sides)
+ *   best_s =  best_t*(1+2^-9) + 2*r_max/|d| + A2         cull slack: the reference's float
+ *             discriminant can move the computed t by <= 1.0e-3*|oc|/|d| and a float-noise
+ *             "hit" of a far sphere can sit <= sqrt(2)*r/|d| before its own box entry.
+ *   Axes with |d| < 1e-30 (incl. the reference's d==0 rule) or a non-finite o*inv_d are
+ *   ignored (NaN operands drop out of FMNMX), i.e. they accept everything, like hit.c:54-56.
+ *
+ * The same source compiles for the host (tests/host_emul) so the logic can be checked against
+ * the oracle without a GPU; that build is test-only and is not part of libsahbvh_b200.so.
+ */
+#ifndef SAHBVH_TRAVERSE_CORE_CUH
+#define SAHBVH_TRAVERSE_CORE_CUH
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SAH_HD __host__ __device__ __forceinline__
+#else
+#define SAH_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+/* explicit round-to-nearest, never contracted into FMA */
+#define F_ADD(a, b) __fadd_rn((a), (b))
+#define F_SUB(a, b) __fsub_rn((a), (b))
+#define F_MUL(a, b) __fmul_rn((a), (b))
+#define F_DIV(a, b) __fdiv_rn((a), (b))
+#define F_SQRT(a) __fsqrt_rn((a))
+#define D_SUB(a, b) __dsub_rn((a), (b))
+#define D_DIV(a, b) __ddiv_rn((a), (b))
+#define D_SQRT(a) __dsqrt_rn((a))
+#define F_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+/* host build: compiled with -ffp-contract=off */
+#define F_ADD(a, b) ((float)((a) + (b)))
+#define F_SUB(a, b) ((float)((a) - (b)))
+#define F_MUL(a, b) ((float)((a) * (b)))
+#define F_DIV(a, b) ((float)((a) / (b)))
+#define F_SQRT(a) ((float)sqrt((double)(a)))
+#define D_SUB(a, b) ((double)(a) - (double)(b))
+#define D_DIV(a, b) ((double)(a) / (double)(b))
+#define D_SQRT(a) sqrt((double)(a))
+#define F_FMA(a, b, c) fmaf((a), (b), (c))
+#endif
+
+#define SAH_EPSILON 0.000001f               /* constants.h:6 */
+#define SAH_REL_BOX 1.00000095367431640625f /* 1 + 2^-20 */
+#define SAH_REL_CULL 1.001953125f           /* 1 + 2^-9  */
+#define SAH_ABS_SCALE 9.5367431640625e-07f  /* 2^-20 */
+#define SAH_TINY_DIR 1e-30f
+#define SAH_STACK_MAX 64
+#define SAH_REF_NONE ((int32_t)0x80000000)
+
+struct SahHit {  /* == gpu_hit */
+    float t;
+    int32_t prim;
+    float px, py, pz;
+    float nx, ny, nz;
+};
+
+struct SahRay {
+    float ox, oy, oz;
+    float dx, dy, dz;
+    float ix, iy, iz;   /* 1/d, NaN on ignored axes */
+    float nx, ny, nz;   /* -(o*inv), NaN on ignored axes */
+    float a;            /* d.d in the reference's order (hit.c:22) */
+    float a2;           /* absolute slack of the conservative box test */
+    float cull_abs;     /* 2*r_max/|d| + a2 */
+};
+
+struct SahCounters {
+    unsigned long long inner, spheres, exact, max_stack;
+};
+
+SAH_HD float sah_nan() {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(0x7fffffff);
+#else
+    return NAN;
+#endif
+}
+
+SAH_HD void sah_axis_setup(float o, float d, float &inv, float &neg_oi) {
+    float i = F_DIV(1.0f, d);
+    float n = -F_MUL(o, i);
+    bool ok = (fabsf(d) >= SAH_TINY_DIR) && (fabsf(n) <= 3.0e38f);
+    inv = ok ? i : sah_nan();
+    neg_oi = ok ? n : sah_nan();
+}
+
+SAH_HD void sah_ray_setup(SahRay &r, float ox, float oy, float oz, float dx, float dy, float dz, float r_max) {
+    r.ox = ox; r.oy = oy; r.oz = oz;
+    r.dx = dx; r.dy = dy; r.dz = dz;
+    sah_axis_setup(ox, dx, r.ix, r.nx);
+    sah_axis_setup(oy, dy, r.iy, r.ny);
+    sah_axis_setup(oz, dz, r.iz, r.nz);
+    r.a = F_ADD(F_ADD(F_MUL(dx, dx), F_MUL(dy, dy)), F_MUL(dz, dz));
+    float m = fmaxf(fmaxf(fabsf(r.nx), fabsf(r.ny)), fabsf(r.nz)); /* NaN operands drop out */
+    if (!(m >= 0.0f)) m = 0.0f;
+    r.a2 = m * SAH_ABS_SCALE;
+    /* 2*r_max/|d|; |d| from the same float sum (exactness irrelevant: slack only) */
+    float len = sqrtf(r.a);
+    float per_d = (len > 0.0f) ? (2.0f * r_max) / len : INFINITY;
+    r.cull_abs = per_d + r.a2;
+}
+
+/* conservative slab test of one box; returns entry distance through tnear */
+SAH_HD bool sah_box_conservative(const SahRay &r, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                 float best_s, float &tnear) {
+    float t1x = F_FMA(lox, r.ix, r.nx), t2x = F_FMA(hix, r.ix, r.nx);
+    float t1y = F_FMA(loy, r.iy, r.ny), t2y = F_FMA(hiy, r.iy, r.ny);
+    float t1z = F_FMA(loz, r.iz, r.nz), t2z = F_FMA(hiz, r.iz, r.nz);
+    float tn = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+    float tf = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+    tn = fmaxf(tn, 0.0f);
+    tf = fminf(F_FMA(tf, SAH_REL_BOX, r.a2), best_s);
+    tnear = tn;
+    return tn <= tf;
+}
+
+/* the reference's slab test, bit for bit (hit.c:49-82) */
+SAH_HD bool sah_box_exact(const SahRay &r, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    const float inf = INFINITY;
+    float t1x, t2x, t1y, t2y, t1z, t2z;
+    if (r.dx == 0.0f) { t1x = -inf; t2x = inf; }
+    else { t1x = F_DIV(F_SUB(lox, r.ox), r.dx); t2x = F_DIV(F_SUB(hix, r.ox), r.dx); }
+    if (r.dy == 0.0f) { t1y = -inf; t2y = inf; }
+    else { t1y = F_DIV(F_SUB(loy, r.oy), r.dy); t2y = F_DIV(F_SUB(hiy, r.oy), r.dy); }
+    if (r.dz == 0.0f) { t1z = -inf; t2z = inf; }
+    else { t1z = F_DIV(F_SUB(loz, r.oz), r.dz); t2z = F_DIV(F_SUB(hiz, r.oz), r.dz); }
+    float tmin = fmaxf(fminf(t1x, t2x), fmaxf(fminf(t1y, t2y), fminf(t1z, t2z)));
+    float tmax = fminf(fmaxf(t1x, t2x), fminf(fmaxf(t1y, t2y), fmaxf(t1z, t2z)));
+    return tmax >= tmin && tmax > SAH_EPSILON;
+}
+
+/* the reference's sphere test up to t (hit.c:21-29); returns true and t when accepted */
+SAH_HD bool sah_sphere_t(const SahRay &r, float cx, float cy, float cz, float rad, float &t_out) {
+    float ocx = F_SUB(r.ox, cx), ocy = F_SUB(r.oy, cy), ocz = F_SUB(r.oz, cz);
+    float b = F_MUL(2.0f, F_ADD(F_ADD(F_MUL(ocx, r.dx), F_MUL(ocy, r.dy)), F_MUL(ocz, r.dz)));
+    float c = F_SUB(F_ADD(F_ADD(F_MUL(ocx, ocx), F_MUL(ocy, ocy)), F_MUL(ocz, ocz)), F_MUL(rad, rad));
+    float disc = F_SUB(F_MUL(b, b), F_MUL(F_MUL(4.0f, r.a), c));
+    if (!(disc > 0.0f)) return false;
+    double num = D_SUB((double)(-b), D_SQRT((double)disc));
+    double den = (double)F_MUL(2.0f, r.a);
+    float t = (float)D_DIV(num, den);
+    if (!(t > SAH_EPSILON)) return false;
+    t_out = t;
+    return true;
+}
+
+/* point and normal of an accepted hit (hit.c:32-33, vec3.c:21-24) */
+SAH_HD void sah_finish_hit(const SahRay &r, float t, int32_t prim, float cx, float cy, float cz, SahHit &h) {
+    float px = F_ADD(r.ox, F_MUL(r.dx, t));
+    float py = F_ADD(r.oy, F_MUL(r.dy, t));
+    float pz = F_ADD(r.oz, F_MUL(r.dz, t));
+    float vx = F_SUB(px, cx), vy = F_SUB(py, cy), vz = F_SUB(pz, cz);
+    float len = F_SQRT(F_ADD(F_ADD(F_MUL(vx, vx), F_MUL(vy, vy)), F_MUL(vz, vz)));
+    h.t = t;
+    h.prim = prim;
+    h.px = px; h.py = py; h.pz = pz;
+    if (len != 0.0f) { h.nx = F_DIV(vx, len); h.ny = F_DIV(vy, len); h.nz = F_DIV(vz, len); }
+    else { h.nx = 0.0f; h.ny = 0.0f; h.nz = 0.0f; }
+}
+
+SAH_HD void sah_miss(SahHit &h) {
+    h.t = 0.0f; h.prim = -1;
+    h.px = h.py = h.pz = 0.0f;
+    h.nx = h.ny = h.nz = 0.0f;
+}
+
+struct SahF4 { float x, y, z, w; };
+
+#if defined(__CUDA_ARCH__)
+SAH_HD SahF4 sah_ld4(const float *p) {
+    float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    SahF4 r = {v.x, v.y, v.z, v.w};
+    return r;
+}
+SAH_HD int32_t sah_f2i(float f) { return __float_as_int(f); }
+#else
+SAH_HD SahF4 sah_ld4(const float *p) {
+    SahF4 r = {p[0], p[1], p[2], p[3]};
+    return r;
+}
+SAH_HD int32_t sah_f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+#endif
+
+/* leaf candidate: sphere test first (cheap reject), exact box test only for a would-be winner */
+template <bool COUNT>
+SAH_HD void sah_leaf(const SahRay &r, const float *__restrict__ spheres4, int n_spheres, int32_t ref,
+                     float lox, float loy, float loz, float hix, float hiy, float hiz,
+                     float &best_t, int32_t &best_prim, float &best_s, SahCounters *cnt) {
+    int32_t idx = ~ref;
+    if ((uint32_t)idx >= (uint32_t)n_spheres) return;   /* one-past-the-end leaf (Q3) / absent child */
+    SahF4 s = sah_ld4(spheres4 + (size_t)idx * 4);
+    if (COUNT) cnt->spheres++;
+    float t;
+    if (!sah_sphere_t(r, s.x, s.y, s.z, s.w, t)) return;
+    bool better = (best_prim < 0) || (t < best_t) || (t == best_t && idx > best_prim);
+    if (!better) return;
+    if (COUNT) cnt->exact++;
+    if (!sah_box_exact(r, lox, loy, loz, hix, hiy, hiz)) return;
+    best_t = t;
+    best_prim = idx;
+    best_s = F_FMA(t, SAH_REL_CULL, r.cull_abs);
+}
+
+/*
+ * One ray through the flattened tree.  `stack` is caller-provided storage of SAH_STACK_MAX ints
+ * with element stride `stride` (1 for a private array, blockDim for a shared-memory column).
+ */
+template <bool COUNT>
+SAH_HD void sah_trace_one(const float *__restrict__ nodes, const float *__restrict__ spheres4, int n_spheres,
+                          const SahRay &r, int32_t *stack, int stride, SahHit &out, SahCounters *cnt) {
+    float best_t = 0.0f, best_s = INFINITY;
+    int32_t best_prim = -1;
+    int sp = 0;
+    int32_t node = 0;
+    for (;;) {
+        const float *w = nodes + (size_t)node * 16;
+        SahF4 w0 = sah_ld4(w), w1 = sah_ld4(w + 4), w2 = sah_ld4(w + 8), w3 = sah_ld4(w + 12);
+        if (COUNT) cnt->inner++;
+        int32_t lref = sah_f2i(w3.x), rref = sah_f2i(w3.y);
+        float tl, tr;
+        bool hl = sah_box_conservative(r, w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, best_s, tl);
+        bool hr = sah_box_conservative(r, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, best_s, tr);
+        if (hl && lref < 0) {
+            sah_leaf<COUNT>(r, spheres4, n_spheres, lref, w0.x, w0.y, w0.z, w0.w, w1.x, w1.y,
+                            best_t, best_prim, best_s, cnt);
+            hl = false;
+        }
+        if (hr && rref < 0) {
+            /* re-check against a best_s the left leaf may just have tightened */
+            if (tr <= best_s)
+                sah_leaf<COUNT>(r, spheres4, n_spheres, rref, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w,
+                                best_t, best_prim, best_s, cnt);
+            hr = false;
+        }
+        if (hl && hr) {
+            bool left_first = tl <= tr;
+            int32_t far_ref = left_first ? rref : lref;
+            node = left_first ? lref : rref;
+            stack[sp * stride] = far_ref;
+            sp++;
+            if (COUNT && (unsigned long long)sp > cnt->max_stack) cnt->max_stack = (unsigned long long)sp;
+        } else if (hl) {
+            node = lref;
+        } else if (hr) {
+            node = rref;
+        } else {
+            if (sp == 0) break;
+            sp--;
+            node = stack[sp * stride];
+        }
+    }
+    if (best_prim >= 0) {
+        SahF4 s = sah_ld4(spheres4 + (size_t)best_prim * 4);
+        sah_finish_hit(r, best_t, best_prim, s.x, s.y, s.z, out);
+    } else {
+        sah_miss(out);
+    }
+}
+
+/* primary-ray constants computed once on the host (ray.c:18-24) */
+struct SahCamera {
+    float px, py, pz;          /* camera->position */
+    float fx, fy, fz;          /* camera->forward */
+    float hx, hy, hz;          /* horizontal = right * (2*half_w) */
+    float vx, vy, vz;          /* vertical   = up * (2*half_h) */
+    float aspect;              /* (float)W/(float)H */
+    float fw, fh;              /* (float)W, (float)H */
+};
+
+/* main.c:362-365 + ray.c:26-31 for pixel (x,y): direction only (origin = position) */
+SAH_HD void sah_primary_dir(const SahCamera &c, int x, int y, float &dx, float &dy, float &dz) {
+    float u = F_MUL(F_SUB(F_DIV((float)x, c.fw), 0.5f), c.aspect);
+    float v = -F_SUB(F_DIV((float)y, c.fh), 0.5f);
+    float ax = F_ADD(c.fx, F_MUL(c.hx, u)), ay = F_ADD(c.fy, F_MUL(c.hy, u)), az = F_ADD(c.fz, F_MUL(c.hz, u));
+    ax = F_ADD(ax, F_MUL(c.vx, v)); ay = F_ADD(ay, F_MUL(c.vy, v)); az = F_ADD(az, F_MUL(c.vz, v));
+    float len = F_SQRT(F_ADD(F_ADD(F_MUL(ax, ax), F_MUL(ay, ay)), F_MUL(az, az)));
+    if (len != 0.0f) { dx = F_DIV(ax, len); dy = F_DIV(ay, len); dz = F_DIV(az, len); }
+    else { dx = 0.0f; dy = 0.0f; dz = 0.0f; }
+}
+
+#endif /* SAHBVH_TRAVERSE_CORE_CUH */

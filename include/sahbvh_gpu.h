@@ -1,0 +1,114 @@
+/*
+ * sahbvh_gpu.h -- the batch C-ABI of libsahbvh_b200.so (plain pointers and sizes only).
+ *
+ * These are the entry points a maintainer of the reference binds in place of the scalar loops
+ *   for ray: ray_bvh_intersect(ray, root)            (benchmark.c:230-245, renderer.c:29-32)
+ *   for y,x: get_camera_ray(...) + trace              (main.c:356-366)
+ * See INTEGRATION.md for the reference-side patch.
+ *
+ * Status codes: 0 = ok, negative = error (SAHBVH_E_*); sahbvh_last_error() returns a
+ * thread-local description.  Nothing here aborts and nothing falls back to the CPU: without a
+ * usable CUDA device every call returns SAHBVH_E_CUDA.
+ */
+#ifndef SAHBVH_GPU_H
+#define SAHBVH_GPU_H
+
+#include "sahbvh_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAHBVH_OK 0
+#define SAHBVH_E_ARG (-1)      /* bad argument (NULL, negative size, pointer outside the sphere array) */
+#define SAHBVH_E_CUDA (-2)     /* CUDA runtime error / no device */
+#define SAHBVH_E_NOMEM (-3)    /* host allocation failed */
+#define SAHBVH_E_DEPTH (-4)    /* tree deeper than the traversal stack supports */
+
+/* 32-byte hit record.  Replaces HitRecord (hit.h:8-14) for batches: `prim` is
+ * hit.object - spheres (the POST-BUILD index) instead of a pointer;
+ * a miss is {t=0, prim=-1, point=0, normal=0} (hit.c:20,92 all-zero record, Q8). */
+typedef struct gpu_hit {
+    float t;
+    int32_t prim;
+    float px, py, pz;
+    float nx, ny, nz;
+} gpu_hit;
+SAHBVH_STATIC_ASSERT(sizeof(gpu_hit) == 32, "gpu_hit layout");
+
+typedef struct gpu_bvh gpu_bvh; /* opaque: flattened tree + SoA spheres resident on ONE device */
+
+typedef struct gpu_bvh_info {
+    int32_t device;
+    int32_t n_spheres;
+    int32_t n_inner;         /* flattened 64-byte inner nodes */
+    int32_t n_leaf_refs;     /* leaves folded into child references */
+    int32_t max_depth;       /* levels below the root */
+    int32_t multi_leaves;    /* leaves with sphere_count > 1 (Q2) */
+    int32_t empty_leaves;    /* leaves with sphere_count == 0 (Q3) */
+    int32_t reserved;
+    float max_radius;
+    float scene_lo[3], scene_hi[3];
+    int64_t device_bytes;
+} gpu_bvh_info;
+
+/* work counters of one traced batch (instrumented kernel variant; not the timed path) */
+typedef struct gpu_trace_stats {
+    uint64_t rays;
+    uint64_t inner_visits;   /* 64-byte nodes fetched            (V_i of SURVEY 8d) */
+    uint64_t sphere_tests;   /* 16-byte spheres fetched + tested (V_s of SURVEY 8d) */
+    uint64_t exact_box_tests;
+    uint64_t hits;
+    uint64_t max_stack;
+} gpu_trace_stats;
+
+const char *sahbvh_last_error(void);
+int sahbvh_device_count(void);
+const char *sahbvh_version(void);
+
+/* Flatten the pointer tree produced by build_bvh_node (reference's or ours) and upload it.
+ *   permuted : the sphere array AFTER the build permuted it (bvh.c:172-201), n entries
+ *   root     : tree whose leaf `sphere` pointers alias `permuted` (bvh.c:133)
+ *   device   : CUDA ordinal, or -1 for the current device
+ * The handle owns copies; host arrays may be freed after the call. */
+int gpu_bvh_upload(const Sphere *permuted, int n, const BVHNode *root, int device, gpu_bvh **out);
+
+/* Build (host, binned SAH, identical topology and permutation to bvh.c:117-209) directly into
+ * the flattened form, skipping the per-node mallocs, then upload.  Permutes spheres[start,end)
+ * in place exactly like build_bvh_node; n_total is the array length (indices are global). */
+int gpu_bvh_build(Sphere *spheres, int n_total, int start, int end, int depth, int device, gpu_bvh **out);
+
+void gpu_bvh_free(gpu_bvh *bvh);
+int gpu_bvh_get_info(const gpu_bvh *bvh, gpu_bvh_info *info);
+
+/* Closest hit for a ray buffer.  HOST buffers: H2D copy of rays, kernel, D2H copy of hits,
+ * chunked over two streams.  Replaces the loop at benchmark.c:230-245 / renderer.c:29-32. */
+int gpu_trace_closest_hit(gpu_bvh *bvh, const Ray *rays, int64_t n, gpu_hit *out);
+/* Same with DEVICE buffers on `stream` (a cudaStream_t, NULL = default); asynchronous. */
+int gpu_trace_closest_hit_dev(gpu_bvh *bvh, const void *d_rays, int64_t n, void *d_out, void *stream);
+
+/* Fused ray generation + closest hit for image rows [y0,y1) of a width x height frame:
+ * pixel (x,y) -> u=((float)x/W-0.5f)*aspect, v=(float)y/H-0.5f, get_camera_ray(cam,u,-v)
+ * (main.c:356-365 + ray.c:17-32, bit-exact), hit written at out[(y-y0)*width + x]. */
+int gpu_trace_primary(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out);
+int gpu_trace_primary_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
+                          void *d_out, void *stream);
+/* Ray generation only (parity aid for ray.c): writes Ray records for rows [y0,y1). */
+int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out, int device);
+
+/* Brute-force closest hit over all n spheres (renderer.c:33-44 semantics: ties -> LOWEST index).
+ * Parity aid for small n. */
+int gpu_trace_brute_force(gpu_bvh *bvh, const Ray *rays, int64_t n, gpu_hit *out);
+
+/* Instrumented trace (counts work per ray; slower; same hits). */
+int gpu_trace_closest_hit_stats(gpu_bvh *bvh, const void *d_rays, int64_t n, void *d_out, gpu_trace_stats *stats);
+int gpu_trace_primary_stats(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
+                            void *d_out, gpu_trace_stats *stats);
+
+/* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
+uint64_t sahbvh_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAHBVH_GPU_H */

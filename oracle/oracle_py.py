@@ -120,12 +120,14 @@ class Oracle:
     def build(self, spheres, start, end, depth=0):
         """Permutes ``spheres`` in place; returns the preorder node array."""
         cap = max(4, 2 * max(end - start, 1) + 4 + 2 * 64)
+        backup = spheres.copy()
         while True:
             nodes = np.zeros(cap, NODE_DT)
             n = self.lib.orc_build(_ptr(spheres), C.c_int(start), C.c_int(end), C.c_int(depth), _ptr(nodes), C.c_int64(cap))
             if n >= 0:
                 return nodes[:n].copy()
-            raise RuntimeError("orc_build overflow")
+            spheres[:] = backup      # degenerate trees (Q2/Q3 chains) can exceed 2n nodes: retry larger
+            cap *= 4
 
     def tree_stats(self, nodes, depth0=0):
         st = Stats()

@@ -1,0 +1,86 @@
+"""Shared helpers for the tests (test infrastructure only)."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+PKG_DIR = os.path.join(ROOT, "cs201_sah-bvh_ray_tracer_b200")
+from oracle.oracle_py import HIT_DT, NODE_DT, RAY_DT, SPHERE_DT, CAMERA_DT, _ptr  # noqa: E402,F401
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def same(a, b):
+    return np.ascontiguousarray(a).tobytes() == np.ascontiguousarray(b).tobytes()
+
+
+def mismatching_rows(a, b):
+    a = np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)
+    b = np.ascontiguousarray(b).view(np.uint8).reshape(len(b), -1)
+    return np.nonzero((a != b).any(axis=1))[0]
+
+
+def assert_hits_equal(got, want, what=""):
+    """Bit-exact comparison of 32-byte hit records (integer index AND float payload)."""
+    assert len(got) == len(want)
+    bad = mismatching_rows(got, want)
+    if len(bad):
+        i = int(bad[0])
+        raise AssertionError(f"{what}: {len(bad)} of {len(got)} hit records differ; first at {i}: got {got[i]} want {want[i]}")
+
+
+class HostEmul:
+    """tests/host_emul/libsahbvh_host_emul.so: csrc/traverse_core.cuh compiled for the host (test-only)."""
+
+    def __init__(self):
+        so = os.path.join(ROOT, "tests", "host_emul", "libsahbvh_host_emul.so")
+        srcs = [os.path.join(ROOT, "tests", "host_emul", "emul.cpp"),
+                os.path.join(PKG_DIR, "csrc", "traverse_core.cuh"),
+                os.path.join(PKG_DIR, "csrc", "flatten.c"),
+                os.path.join(PKG_DIR, "csrc", "sah_builder.c"),
+                os.path.join(PKG_DIR, "csrc", "host_ref_api.c")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["make", "-s", "-C", PKG_DIR, "emul"])
+        self.lib = C.CDLL(so)
+        self.lib.emul_build.restype = C.c_void_p
+        self.lib.emul_from_pointers.restype = C.c_void_p
+        self.lib.emul_build_tree.restype = C.c_int64
+
+    def build_tree(self, spheres, start, end, depth):
+        cap = 64 * max(end - start, 1) + 1024
+        out = np.zeros(cap, NODE_DT)
+        used = self.lib.emul_build_tree(_ptr(spheres), C.c_int(start), C.c_int(end), C.c_int(depth), _ptr(out), C.c_int64(cap))
+        assert used > 0
+        return out[:used].copy()
+
+    def build(self, spheres, n_total, start, end, depth):
+        h = self.lib.emul_build(_ptr(spheres), C.c_int(n_total), C.c_int(start), C.c_int(end), C.c_int(depth))
+        assert h
+        return h
+
+    def from_pointers(self, spheres, n, root):
+        h = self.lib.emul_from_pointers(_ptr(spheres), C.c_int(n), C.c_void_p(root))
+        assert h
+        return h
+
+    def free(self, h):
+        self.lib.emul_free(C.c_void_p(h))
+
+    def trace(self, h, rays, threads=8):
+        rays = np.ascontiguousarray(rays)
+        hits = np.zeros(len(rays), HIT_DT)
+        st = (C.c_uint64 * 6)()
+        self.lib.emul_trace(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), _ptr(hits), st, C.c_int(threads))
+        stats = dict(zip(("rays", "inner_visits", "sphere_tests", "exact_box_tests", "hits", "max_stack"), map(int, st)))
+        return hits, stats
+
+    def primary_rays(self, cam, w, h, y0=0, y1=None):
+        y1 = h if y1 is None else y1
+        out = np.zeros((y1 - y0) * w, RAY_DT)
+        self.lib.emul_primary_rays(_ptr(cam), C.c_int(w), C.c_int(h), C.c_int(y0), C.c_int(y1), _ptr(out))
+        return out

@@ -1,0 +1,138 @@
+/*
+ * tests/host_emul/emul.cpp -- TEST-ONLY host build of the per-ray traversal core.
+ *
+ * Compiles csrc/traverse_core.cuh (the exact source the CUDA kernels use) with g++ so that the
+ * flattener, the conservative interior test, the tie rule and the primary-ray arithmetic can be
+ * checked against the oracle in this GPU-less container.  It is NOT part of
+ * libsahbvh_b200.so, exports only emul_* symbols, and nothing in the product links it.
+ */
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <thread>
+
+#include "sahbvh_internal.h"
+#include "traverse_core.cuh"
+
+/* the product's scalar GPU hooks are not available in this build */
+extern "C" int sahbvh_scalar_trace(const BVHNode *, const Ray *, HitRecord *)
+{
+    sahbvh_set_error("host emulation build has no GPU");
+    return SAHBVH_E_CUDA;
+}
+extern "C" void sahbvh_scalar_forget(const BVHNode *) {}
+
+struct emul_bvh {
+    flat_bvh f;
+};
+
+static emul_bvh *wrap(sah_tree *t, const Sphere *spheres, int n, int rc)
+{
+    emul_bvh *e = nullptr;
+    if (rc == SAHBVH_OK) {
+        e = (emul_bvh *)calloc(1, sizeof(emul_bvh));
+        rc = flat_bvh_from_tree(&e->f, t, spheres, n);
+        if (rc != SAHBVH_OK) { free(e); e = nullptr; }
+    }
+    sah_tree_free(t);
+    return e;
+}
+
+extern "C" emul_bvh *emul_from_pointers(const Sphere *permuted, int n, const BVHNode *root)
+{
+    sah_tree t;
+    if (sah_tree_init(&t, 2 * (int64_t)(n > 0 ? n : 1) + 16) != SAHBVH_OK) return nullptr;
+    return wrap(&t, permuted, n, sah_tree_from_pointers(&t, root, permuted, n));
+}
+
+extern "C" emul_bvh *emul_build(Sphere *spheres, int n_total, int start, int end, int depth)
+{
+    sah_tree t;
+    if (sah_tree_init(&t, 2 * (int64_t)(end - start + 1) + 16) != SAHBVH_OK) return nullptr;
+    return wrap(&t, spheres, n_total, sah_build(&t, spheres, start, end, depth));
+}
+
+/* preorder export of the product builder's tree (compared with the oracle/reference tree) */
+extern "C" int64_t emul_build_tree(Sphere *spheres, int start, int end, int depth, sah_node *out, int64_t cap)
+{
+    sah_tree t;
+    if (sah_tree_init(&t, 2 * (int64_t)(end - start + 1) + 16) != SAHBVH_OK) return -1;
+    int64_t used = -1;
+    if (sah_build(&t, spheres, start, end, depth) == SAHBVH_OK && t.used <= cap) {
+        memcpy(out, t.nodes, (size_t)t.used * sizeof(sah_node));
+        used = t.used;
+    }
+    sah_tree_free(&t);
+    return used;
+}
+
+extern "C" void emul_free(emul_bvh *e)
+{
+    if (!e) return;
+    flat_bvh_release(&e->f);
+    free(e);
+}
+
+extern "C" void emul_info(const emul_bvh *e, gpu_bvh_info *info) { *info = e->f.info; }
+
+static void trace_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t hi, gpu_hit *out, SahCounters *cnt)
+{
+    int32_t stack[SAH_STACK_MAX];
+    for (int64_t i = lo; i < hi; i++) {
+        SahRay r;
+        sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
+                      rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, e->f.info.max_radius);
+        SahHit h;
+        sah_trace_one<true>(e->f.nodes, e->f.spheres4, e->f.info.n_spheres, r, stack, 1, h, cnt);
+        memcpy(&out[i], &h, sizeof h);
+    }
+}
+
+extern "C" void emul_trace(const emul_bvh *e, const Ray *rays, int64_t n, gpu_hit *out, gpu_trace_stats *stats, int threads)
+{
+    if (threads < 1) threads = 1;
+    std::vector<SahCounters> cnt((size_t)threads, SahCounters{0, 0, 0, 0});
+    std::vector<std::thread> pool;
+    for (int k = 0; k < threads; k++)
+        pool.emplace_back(trace_range, e, rays, n * k / threads, n * (k + 1) / threads, out, &cnt[(size_t)k]);
+    for (auto &t : pool) t.join();
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->rays = (uint64_t)n;
+        for (auto &c : cnt) {
+            stats->inner_visits += c.inner;
+            stats->sphere_tests += c.spheres;
+            stats->exact_box_tests += c.exact;
+            if (c.max_stack > stats->max_stack) stats->max_stack = c.max_stack;
+        }
+        for (int64_t i = 0; i < n; i++) stats->hits += out[i].prim >= 0;
+    }
+}
+
+static void fill_camera(const Camera *cam, int width, int height, SahCamera *c)
+{
+    float aspect = (float)width / (float)height;
+    float fov_rad = (float)((double)cam->fov * (M_PI / (double)180.0f));
+    float half_h = (float)tan((double)(fov_rad / 2.0f));
+    float half_w = aspect * half_h;
+    Vec3 horizontal = vec3_multiply(cam->right, 2.0f * half_w);
+    Vec3 vertical = vec3_multiply(cam->up, 2.0f * half_h);
+    c->px = cam->position.x; c->py = cam->position.y; c->pz = cam->position.z;
+    c->fx = cam->forward.x; c->fy = cam->forward.y; c->fz = cam->forward.z;
+    c->hx = horizontal.x; c->hy = horizontal.y; c->hz = horizontal.z;
+    c->vx = vertical.x; c->vy = vertical.y; c->vz = vertical.z;
+    c->aspect = aspect; c->fw = (float)width; c->fh = (float)height;
+}
+
+extern "C" void emul_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out)
+{
+    SahCamera c;
+    fill_camera(cam, width, height, &c);
+    for (int y = y0; y < y1; y++)
+        for (int x = 0; x < width; x++) {
+            Ray *r = &out[(size_t)(y - y0) * (size_t)width + (size_t)x];
+            r->origin = cam->position;
+            sah_primary_dir(c, x, y, r->direction.x, r->direction.y, r->direction.z);
+        }
+}

@@ -1,0 +1,347 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C-ABI of
+libsahbvh_b200.so (ctypes); the checker is the oracle (oracle/liboracle.so) and the golden
+fixtures generated from the compiled reference.  Bar: hit records BIT-EXACT (index, t, point,
+normal) -- tighter than the 1e-5 relative tolerance north_star allows for t/normal.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import HIT_DT, RAY_DT, SPHERE_DT, _ptr, assert_hits_equal, same, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(pkg):
+    if pkg.device_count() < 1:
+        pytest.fail("no CUDA device: the closest-hit path has no CPU fallback")
+    return pkg
+
+
+# ---------------------------------------------------------------- config 2: default renderer scene
+@pytest.mark.parametrize("seed", [1, 7, 649, 1164])
+def test_default_scene_frame(gpu, oracle, golden, seed):
+    answers, _ = golden
+    case = answers["cases"][f"default_seed{seed}"]
+    gpu.srand(seed)
+    s = gpu.random_scene(20)
+    bvh = gpu.GpuBvh.build(s, 20, 0, 20, 0)
+    info = bvh.info()
+    assert info["empty_leaves"] == case["tree"]["empty_leaves"] and info["multi_leaves"] == case["tree"]["multi_leaves"]
+    assert sha(s[:20]) == case["sha_scene_post_build"]
+    cam = gpu.default_camera()
+    hits = bvh.trace_primary(cam, 800, 600)
+    assert int((hits["prim"] >= 0).sum()) == case["hits"]
+    assert sha(hits) == case["sha_hits"]
+    # live oracle on the same inputs
+    oracle.srand(seed)
+    so = oracle.scene_random(20)
+    nodes = oracle.build(so, 0, 20, 0)
+    want, _ = oracle.trace_bvh(nodes, so, 20, oracle.primary_rays(cam, 800, 600))
+    assert_hits_equal(hits, want, f"default scene seed {seed}")
+    # brute force kernel == renderer.c:33-44 (ties -> lowest index)
+    rays = oracle.primary_rays(cam, 800, 600)
+    brute = bvh.trace_brute_force(rays)
+    assert sha(brute) == case["sha_brute_hits"]
+    bvh.close()
+
+
+# ---------------------------------------------------------------- config 1: benchmark.c as shipped
+@pytest.mark.parametrize("n", [5000, 50000])
+def test_benchmark_as_shipped(gpu, golden, n):
+    answers, vec = golden
+    name = f"bench_{n}_asshipped"
+    case = answers["cases"][name]
+    gpu.srand(1)
+    s = gpu.benchmark_scene(n)
+    root = gpu.build_bvh_node(s, 0, n - 1, 20)          # benchmark.c:317 (Q10)
+    rays = gpu.benchmark_rays(10000)                    # same rand() stream, benchmark.c:232-240
+    assert sha(s[:n]) == case["sha_scene_post_build"] and sha(rays) == case["sha_rays"]
+    bvh = gpu.GpuBvh.upload(s, n, root)
+    hits = bvh.trace_closest_hit(rays)
+    assert int((hits["prim"] >= 0).sum()) == case["hits"]
+    assert sha(hits) == case["sha_hits"]
+    idx = vec[f"{name}__idx"]
+    assert_hits_equal(hits[idx], vec[f"{name}__hits"], name)
+    bvh.close()
+    gpu.free_bvh(root)
+
+
+# ---------------------------------------------------------------- config 3: 100 K spheres, 4K primary
+@pytest.fixture(scope="module")
+def scene100k(gpu, oracle):
+    gpu.srand(1)
+    s = gpu.benchmark_scene(100000)
+    bvh = gpu.GpuBvh.build(s, 100000, 0, 100000, 0)
+    rays = gpu.benchmark_rays(100000)
+    oracle.srand(1)         # the oracle rebuilds the same tree from the same seed
+    so = oracle.scene_benchmark(100000)
+    nodes = oracle.build(so, 0, 100000, 0)
+    assert same(so, s)
+    yield bvh, s, rays, nodes
+    bvh.close()
+
+
+def test_100k_ray_buffer(gpu, golden, scene100k):
+    answers, vec = golden
+    bvh, s, rays, _ = scene100k
+    case = answers["cases"]["bench_100000_full"]
+    assert sha(rays) == case["sha_rays"]
+    hits = bvh.trace_closest_hit(rays)
+    assert int((hits["prim"] >= 0).sum()) == case["hits"] == 4741
+    assert sha(hits) == case["sha_hits"]
+    # ragged sizes and order independence
+    for m in (1, 31, 129, 4097):
+        assert_hits_equal(bvh.trace_closest_hit(rays[:m]), hits[:m], f"ragged {m}")
+    perm = np.random.default_rng(0).permutation(len(rays))
+    assert_hits_equal(bvh.trace_closest_hit(rays[perm]), hits[perm], "permuted ray order")
+    assert len(bvh.trace_closest_hit(rays[:0])) == 0
+
+
+def test_100k_primary_4k(gpu, oracle, golden, scene100k):
+    answers, vec = golden
+    bvh, s, _, nodes = scene100k
+    cam = gpu.default_camera()
+    W, H = 3840, 2160
+    hits = bvh.trace_primary(cam, W, H)
+    case = answers["cases"]["bench_100000_primary4k_sample"]
+    assert_hits_equal(hits[::997], vec["bench_100000_primary4k_sample__hits"], "4K sample vs golden")
+    assert int((hits[::997]["prim"] >= 0).sum()) == case["hits"]
+    # live oracle on a random pixel sample, including the dir.y==0 row and dir.x==0 column (pathological rays)
+    rng = np.random.default_rng(3)
+    idx = np.unique(np.concatenate([rng.integers(0, W * H, 30000), (H // 2) * W + np.arange(0, W, 16),
+                                    np.arange(0, H, 16) * W + W // 2]))
+    rays = gpu.generate_primary_rays(cam, W, H)
+    assert sha(rays) == case["sha_rays_full_frame"]
+    want, _ = oracle.trace_bvh(nodes, s, 100000, rays[idx])
+    assert_hits_equal(hits[idx], want, "4K random sample vs oracle")
+    # properties at full size: row bands == full frame; ray-buffer kernel == fused kernel
+    for y0, y1 in ((0, 8), (1000, 1007), (2152, 2160), (3, 1083)):
+        band = bvh.trace_primary(cam, W, H, y0, y1)
+        assert_hits_equal(band, hits[y0 * W:y1 * W], f"band [{y0},{y1})")
+    assert_hits_equal(bvh.trace_closest_hit(rays), hits, "ray buffer vs fused primary")
+    # hit-record invariants (size independent)
+    h = hits[hits["prim"] >= 0]
+    c = s["c"][h["prim"]]
+    r = s["r"][h["prim"]]
+    assert np.all(h["t"] > 1e-6)
+    assert np.allclose(np.linalg.norm(h["n"], axis=1), 1.0, atol=1e-5)
+    assert np.allclose(np.linalg.norm(h["p"] - c, axis=1), r, rtol=0, atol=0.2)   # float-noise t
+    miss = hits[hits["prim"] < 0]
+    assert not miss.view(np.uint8).reshape(len(miss), 32)[:, 8:].any() and not miss["t"].any()
+
+
+def test_100k_bounce_rays(gpu, oracle, golden, scene100k):
+    answers, vec = golden
+    bvh, s, _, nodes = scene100k
+    cam = gpu.default_camera()
+    h8 = bvh.trace_primary(cam, 800, 600)
+    case = answers["cases"]["bench_100000_bounce"]
+    assert sha(h8) == case["sha_primary_hits_800x600"]
+    gpu.srand(5)
+    br = gpu.bounce_rays(h8)                              # renderer.c:51-54 on the host, serial rand()
+    assert sha(br) == case["sha_rays"]
+    bh = bvh.trace_closest_hit(br)
+    assert sha(bh) == case["sha_hits"]
+    assert_hits_equal(bh[:4096], vec["bench_100000_bounce__hits"], "bounce")
+
+
+def test_100k_bvh_vs_brute_force_on_gpu(gpu, scene100k):
+    bvh, s, rays, _ = scene100k
+    sub = rays[:8192]
+    a = bvh.trace_closest_hit(sub)
+    b = bvh.trace_brute_force(sub)
+    assert same(a["t"], b["t"])
+    assert (a["prim"] >= b["prim"]).all()         # ties: BVH -> larger index, brute force -> lower
+
+
+# ---------------------------------------------------------------- 1 M spheres (north-star scene)
+@pytest.fixture(scope="module")
+def scene1m(gpu):
+    gpu.srand(1)
+    s = gpu.benchmark_scene(1000000)
+    bvh = gpu.GpuBvh.build(s, 1000000, 0, 1000000, 0)
+    rays = gpu.benchmark_rays(100000)
+    yield bvh, s, rays
+    bvh.close()
+
+
+def test_1m_golden(gpu, golden, scene1m):
+    answers, vec = golden
+    bvh, s, rays = scene1m
+    case = answers["cases"]["bench_1000000_full"]
+    info = bvh.info()
+    assert info["n_inner"] == 999999 and info["max_depth"] == case["tree"]["max_depth"] == 23
+    assert sha(s[:1000000]) == case["sha_scene_post_build"]
+    assert sha(rays) == case["sha_rays"]
+    hits = bvh.trace_closest_hit(rays)
+    assert int((hits["prim"] >= 0).sum()) == case["hits"] == 38847
+    assert sha(hits) == case["sha_hits"]
+    assert_hits_equal(hits[vec["bench_1000000_full__idx"]], vec["bench_1000000_full__hits"], "1M sample")
+
+
+def test_1m_primary_and_bounce_vs_oracle(gpu, oracle, scene1m):
+    bvh, s, _ = scene1m
+    oracle.srand(1)
+    so = oracle.scene_benchmark(1000000)
+    nodes = oracle.build(so, 0, 1000000, 0)
+    assert same(so, s)
+    cam = gpu.default_camera()
+    W, H = 3840, 2160
+    hits = bvh.trace_primary(cam, W, H)
+    rng = np.random.default_rng(11)
+    idx = np.unique(np.concatenate([rng.integers(0, W * H, 6000), (H // 2) * W + np.arange(0, W, 64)]))
+    rays = oracle.primary_rays(cam, W, H)
+    want, _ = oracle.trace_bvh(nodes, so, 1000000, rays[idx])
+    assert_hits_equal(hits[idx], want, "1M 4K sample vs oracle")
+    assert 0.35 < (hits["prim"] >= 0).mean() < 0.45
+    # incoherent diffuse-bounce rays (config 4 recipe) from the frame's hits
+    gpu.srand(9)
+    br = gpu.bounce_rays(hits[::200])
+    bh = bvh.trace_closest_hit(br)
+    want, _ = oracle.trace_bvh(nodes, so, 1000000, br[:5000])
+    assert_hits_equal(bh[:5000], want, "1M bounce vs oracle")
+    b = bvh.trace_brute_force(br[:2048])
+    assert same(bh[:2048]["t"], b["t"])
+
+
+# ---------------------------------------------------------------- edge cases
+def test_tiny_trees_and_zero_directions(gpu, oracle):
+    for n in (0, 1, 2, 3):
+        oracle.srand(40 + n)
+        so = oracle.scene_random(n)
+        s = so.copy()
+        nodes = oracle.build(so, 0, n, 0)
+        bvh = gpu.GpuBvh.build(s, n, 0, n, 0)
+        cam = gpu.default_camera()
+        hits = bvh.trace_primary(cam, 320, 240)
+        want, _ = oracle.trace_bvh(nodes, so, n, oracle.primary_rays(cam, 320, 240))
+        assert_hits_equal(hits, want, f"n={n}")
+        bvh.close()
+    oracle.srand(2)
+    so = oracle.scene_random(400)
+    s = so.copy()
+    nodes = oracle.build(so, 0, 400, 0)
+    bvh = gpu.GpuBvh.build(s, 400, 0, 400, 0)
+    dirs = [(0, 0, -1), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, -1), (0, 1, -1), (1, 1, 0), (0, 0, 0),
+            (1e-38, 0, -1), (1e-31, 1e-20, -1), (-0.0, 0.0, -1), (1e-45, 1e-45, -1), (3e-39, 1, 1e-39)]
+    lst = [((ox, oy, oz), d) for ox in (-30.0, 0.0, 12.5) for oy in (-10.0, 4.0) for oz in (50.0, 0.0, -3.0) for d in dirs]
+    rays = np.zeros(len(lst), RAY_DT)
+    for i, (o, d) in enumerate(lst):
+        rays[i]["o"] = o
+        rays[i]["d"] = d
+    want, _ = oracle.trace_bvh(nodes, so, 400, rays)
+    assert_hits_equal(bvh.trace_closest_hit(rays), want, "zero/tiny direction components")
+    # origins inside spheres / far away / unnormalised directions
+    rng = np.random.default_rng(0)
+    m = 20000
+    rays = np.zeros(m, RAY_DT)
+    rays["o"] = so["c"][rng.integers(0, 400, m)] + rng.normal(size=(m, 3)).astype(np.float32) * \
+        rng.choice([0.0, 0.5, 5.0, 3000.0], size=(m, 1)).astype(np.float32)
+    rays["d"] = rng.normal(size=(m, 3)).astype(np.float32) * rng.choice([1e-3, 1.0, 1e3], size=(m, 1)).astype(np.float32)
+    want, _ = oracle.trace_bvh(nodes, so, 400, rays)
+    assert_hits_equal(bvh.trace_closest_hit(rays), want, "inside/far/unnormalised")
+    bvh.close()
+
+
+def test_multi_sphere_leaves_5000(gpu, golden):
+    answers, _ = golden
+    case = answers["cases"]["random5000_seed3"]
+    gpu.srand(3)
+    s = gpu.random_scene(5000)
+    bvh = gpu.GpuBvh.build(s, 5000, 0, 5000, 0)
+    info = bvh.info()
+    assert info["multi_leaves"] == case["tree"]["multi_leaves"] and info["empty_leaves"] == case["tree"]["empty_leaves"]
+    rays = gpu.generate_primary_rays(gpu.default_camera(), 800, 600)[::7].copy()
+    assert sha(rays) == case["sha_rays"]
+    assert sha(bvh.trace_closest_hit(rays)) == case["sha_hits"]
+    bvh.close()
+
+
+def test_generated_rays_and_moved_camera(gpu, oracle, golden):
+    answers, vec = golden
+    cam = gpu.default_camera()
+    for w, h in ((800, 600), (1023, 517), (7, 3), (33, 9)):
+        assert same(gpu.generate_primary_rays(cam, w, h), oracle.primary_rays(cam, w, h))
+    cam2 = vec["camera_update__cam"].copy()
+    assert sha(gpu.generate_primary_rays(cam2, 800, 600)) == answers["camera_update"]["sha_rays_800x600"]
+    assert same(gpu.generate_primary_rays(cam2, 640, 360, 8, 64), oracle.primary_rays(cam2, 640, 360, 8, 64))
+
+
+def test_error_codes(gpu):
+    h = C.c_void_p()
+    assert gpu.lib.gpu_bvh_upload(None, 5, None, -1, C.byref(h)) == -1
+    assert b"NULL" in gpu.lib.sahbvh_last_error()
+    gpu.srand(1)
+    s = gpu.benchmark_scene(64)
+    assert gpu.lib.gpu_bvh_build(_ptr(s), 64, 0, 65, 0, -1, C.byref(h)) == -1
+    assert gpu.lib.gpu_bvh_build(_ptr(s), 64, 0, 64, 0, 99, C.byref(h)) == -1
+    bvh = gpu.GpuBvh.build(s, 64, 0, 64, 0)
+    assert gpu.lib.gpu_trace_closest_hit(bvh._h, None, C.c_int64(5), None) == -1
+    assert gpu.lib.gpu_trace_primary(bvh._h, _ptr(gpu.default_camera()), 0, 10, 0, 10, _ptr(s)) == -1
+    bvh.close()
+
+
+def test_scalar_drop_in_ray_bvh_intersect(gpu, oracle):
+    """hit.h:18 signature, by value, GPU-backed: identical HitRecord, object pointer into the caller's array."""
+    class V(C.Structure):
+        _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+    class RayS(C.Structure):
+        _fields_ = [("o", V), ("d", V)]
+
+    class Rec(C.Structure):
+        _fields_ = [("t", C.c_float), ("p", V), ("n", V), ("hit", C.c_int), ("obj", C.c_void_p)]
+
+    gpu.lib.ray_bvh_intersect.restype = Rec
+    gpu.lib.ray_bvh_intersect.argtypes = [RayS, C.c_void_p]
+    oracle.srand(7)
+    so = oracle.scene_random(20)
+    s = so.copy()
+    nodes = oracle.build(so, 0, 20, 0)
+    root = gpu.build_bvh_node(s, 0, 20, 0)
+    rays = oracle.primary_rays(gpu.default_camera(), 800, 600)[::4801]
+    want, _ = oracle.trace_bvh(nodes, so, 20, rays)
+    base = s.ctypes.data
+    nhit = 0
+    for i, r in enumerate(rays):
+        rec = gpu.lib.ray_bvh_intersect(RayS(V(*r["o"]), V(*r["d"])), C.c_void_p(root))
+        assert rec.hit == int(want["prim"][i] >= 0)
+        if rec.hit:
+            nhit += 1
+            assert rec.obj == base + 20 * int(want["prim"][i])
+            got = np.array([rec.t, rec.p.x, rec.p.y, rec.p.z, rec.n.x, rec.n.y, rec.n.z], np.float32)
+            assert got.tobytes() == np.array([want["t"][i], *want["p"][i], *want["n"][i]], np.float32).tobytes()
+        else:
+            assert rec.t == 0 and rec.obj is None
+    assert nhit > 5
+    gpu.free_bvh(root)
+
+
+def test_device_pointer_api_and_counters(gpu, oracle, emul, scene100k):
+    import torch
+    bvh, s, rays, nodes = scene100k
+    sub = np.ascontiguousarray(rays[:50000])
+    d_rays = torch.from_numpy(sub.view(np.float32).reshape(-1, 6)).cuda()
+    d_hits = torch.empty((len(sub), 8), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    before = gpu.kernel_launches()
+    bvh.trace_closest_hit_dev(d_rays.data_ptr(), len(sub), d_hits.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert gpu.kernel_launches() == before + 1
+    got = d_hits.cpu().numpy().view(HIT_DT).reshape(-1)
+    want = bvh.trace_closest_hit(sub)
+    assert_hits_equal(got, want, "device-pointer API")
+    stats = bvh.trace_closest_hit_stats(d_rays.data_ptr(), len(sub), d_hits.data_ptr())
+    assert_hits_equal(d_hits.cpu().numpy().view(HIT_DT).reshape(-1), want, "instrumented kernel")
+    # the same traversal core compiled for the host must count the same work
+    oracle.srand(1)
+    sp = oracle.scene_benchmark(100000)
+    h = emul.build(sp, 100000, 0, 100000, 0)
+    _, est = emul.trace(h, sub)
+    emul.free(h)
+    for k in ("inner_visits", "sphere_tests", "exact_box_tests", "hits"):
+        assert stats[k] == est[k], (k, stats, est)
+    assert stats["max_stack"] == est["max_stack"]
