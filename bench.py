@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- closest-hit throughput of the SAH-BVH path on B200 (contract in the task brief).
+
+Headline workload (config.workload): the scene north_star's target is quoted on --
+1 M random spheres (benchmark.c:306-314 recipe, srand(1)), SAH BVH `build(0,n,0)`,
+3840x2160 primary rays of the default camera (main.c:203-211, :356-365), one closest-hit
+query per pixel.  One "step" = one full frame through the fused ray-generation + traversal
+kernel, hit records (32 B/ray) written to HBM.  `sweep` adds the other single-GPU
+configurations (default 20-sphere scene 800x600, 100 K spheres 4K primary, 1 M spheres
+incoherent diffuse-bounce rays) measured the same way.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-sweep]
+
+N > 1: launched under torchrun, one rank per GPU; the BVH is replicated (every rank builds the
+same tree from the same seed), rows are sharded in contiguous bands, every rank traces ITS band
+of a full frame per step ("weak": per-GPU work fixed = one full 4K frame's worth of rows per
+rank, the frame height grows with N) and an NCCL all_gather assembles the frame buffer.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SPHERES = 1_000_000
+WIDTH, HEIGHT = 3840, 2160
+METRIC = "closest_hit_grays_per_s"
+UNIT = "Grays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--spheres", type=int, default=N_SPHERES)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_spheres, width, height, row_step, threads, steps=1, warmup=0):
+    """Times the reference's ray_bvh_intersect loop (oracle/_ref = the unmodified reference
+    sources; falls back to the oracle port if the prebuilt library is absent) over a bounded
+    sample of the headline workload: every `row_step`-th image row of the 4K primary frame."""
+    from oracle.oracle_py import Oracle, RefLib, ref_available
+    orc = Oracle()
+    use_ref = ref_available()     # rays come from the oracle's run-time W/H ray generator (pinned bit-exact to ray.c)
+    cam = orc.default_camera()
+    rows = list(range(0, height, row_step))
+    rays = np.concatenate([orc.primary_rays(cam, width, height, y, y + 1) for y in rows])
+    t_build0 = time.time()
+    if use_ref:
+        R = RefLib()
+        R.srand(1)
+        s = R.scene_benchmark(n_spheres)
+        root, _ = R.build(s, 0, n_spheres, 0)
+        kind = "reference"
+
+        def run():
+            _, sec = R.trace_bvh(root, s, rays, threads)
+            return sec
+    else:
+        orc.srand(1)
+        s = orc.scene_benchmark(n_spheres)
+        nodes = orc.build(s, 0, n_spheres, 0)
+        kind = "port"
+
+        def run():
+            _, sec = orc.trace_bvh(nodes, s, n_spheres, rays, threads)
+            return sec
+    build_s = time.time() - t_build0
+    for _ in range(warmup):
+        run()
+    secs = [run() for _ in range(steps)]
+    sec = float(np.mean(secs))
+    return {"value": len(rays) / sec / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"every {row_step}th row of the {width}x{height} primary frame = {len(rays)} rays per step, "
+                      f"{n_spheres} spheres, ray_bvh_intersect loop only (build {build_s:.1f} s excluded)",
+            "seconds_per_step": sec, "rays_per_step": len(rays)}
+
+
+def frame_dims(world):
+    """Weak scaling: the frame grows with sqrt(N) in each dimension (same field of view and aspect,
+    denser sampling: 4K at N=1, 8K at N=4); W is a multiple of the CTA tile width (32), H of 8*N so
+    that the N row bands are equal and tile aligned."""
+    scale = float(np.sqrt(world))
+    return int(round(WIDTH * scale / 32.0)) * 32, int(round(HEIGHT * scale / (8.0 * world))) * 8 * world
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    W, H = frame_dims(args.gpus)
+    # ~2 s per step at 0.015 Mrays/s/thread (measured: 8 threads on 8 vCPU, 1 M spheres)
+    row_step = max(1, int(round(H * W / (0.015e6 * threads * 2.0))))
+    r = cpu_reference_run(args.spheres, W, H, row_step, threads, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.spheres} random spheres (benchmark.c:306-314 recipe, srand 1), SAH BVH build(0,n,0), "
+                               f"{W}x{H} primary rays of the default camera, closest hit, 32 B hit record per ray",
+                   "sample": r["sample"]},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def time_steps(torch, fn, steps, warmup, flush, dist_on):
+    """W warm-up + K timed steps; per-step CUDA events on the current stream, L2 flushed between
+    steps (outside the timed events); barrier + synchronize on both sides."""
+    for _ in range(warmup):
+        flush()
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    return float(np.sum(ms)), ms
+
+
+def algorithmic(stats, generated, with_input):
+    """bytes/ray = 64 V_i + 16 V_s + B_in + 32 ; FLOP/ray = 48 V_i + 25 V_s + 23 [hit] + 26 [generated]."""
+    rays = max(stats["rays"], 1)
+    vi, vs, hit = stats["inner_visits"] / rays, stats["sphere_tests"] / rays, stats["hits"] / rays
+    return {"V_i": vi, "V_s": vs, "hit_rate": hit,
+            "bytes_per_ray": 64 * vi + 16 * vs + (24 if with_input else 0) + 32,
+            "flop_per_ray": 48 * vi + 25 * vs + 23 * hit + (26 if generated else 0)}
+
+
+def run_b200(args):
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_pkg()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist_on = world > 1
+    if pkg.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the closest-hit path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream().cuda_stream
+    hbm_peak, peak_src, sm_max = measured_peaks()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush():
+        flush_buf.fill_(1)
+
+    # ---- scene + BVH (replicated per GPU: every rank builds the same tree from the same seed)
+    t0 = time.time()
+    pkg.srand(1)
+    spheres = pkg.benchmark_scene(args.spheres)
+    bvh = pkg.GpuBvh.build(spheres, args.spheres, 0, args.spheres, 0, device=local)
+    build_s = time.time() - t0
+    info = bvh.info()
+    cam = pkg.default_camera()
+
+    W, H = frame_dims(world)     # every rank traces one contiguous row band of ~8.3 M rays
+    y0, y1 = pkg.shard_rows(H, rank, world)
+    rows = y1 - y0
+    assert rows * world == H
+    n_local = rows * W
+    frame = torch.empty((world, n_local, 8), dtype=torch.float32, device="cuda")   # all_gather target
+    my_slot = frame[rank]
+
+    def step():
+        bvh.trace_primary_dev(cam, W, H, y0, y1, my_slot.data_ptr(), stream)
+        if dist_on:
+            dist.all_gather_into_tensor(frame.view(-1, 8), my_slot)
+
+    clocks = ClockSampler(local)
+    launches0 = pkg.kernel_launches()
+    # kernel-only duration of the dominant kernel (no collective), for the roofline
+    def kernel_only():
+        bvh.trace_primary_dev(cam, W, H, y0, y1, my_slot.data_ptr(), stream)
+
+    clocks.start()
+    total_ms, per_step = time_steps(torch, step, args.steps, args.warmup, flush, dist_on)
+    clk = clocks.stop()
+    launches = pkg.kernel_launches() - launches0 - args.warmup
+    k_ms, _ = time_steps(torch, kernel_only, max(3, min(args.steps, 10)), 1, flush, False)
+    k_ms /= max(3, min(args.steps, 10))
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist_on:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    total_rays = W * H
+    value = total_rays / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e through the host-buffer C-ABI call (pinned host output; D2H inside the timed region)
+    host_out = torch.empty((n_local, 8), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        bvh.trace_primary_ptr(cam, W, H, y0, y1, host_out.data_ptr())
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t_e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()        # synchronous: returns after the last D2H chunk landed
+    e2e_s = (time.perf_counter() - t_e0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist_on:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = total_rays / float(te.item()) / 1e9
+
+    if rank != 0:
+        if dist_on:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- work counters (instrumented kernel, untimed) -> algorithmic bytes / flops per ray
+    stats = bvh.trace_primary_stats(cam, W, H, y0, y1, my_slot.data_ptr())
+    alg = algorithmic(stats, generated=True, with_input=False)
+    peaks = pkg.measure_peaks(local)
+    k_s = k_ms * 1e-3
+    ach_gbs = alg["bytes_per_ray"] * n_local / k_s / 1e9
+    ach_tflops = alg["flop_per_ray"] * n_local / k_s / 1e12
+    compulsory = (32 * n_local + info["n_inner"] * 64 + info["n_spheres"] * 16) / k_s / 1e9
+    roofline = {
+        "kernel": "k_trace_primary", "bound": "l2",
+        "achieved": ach_gbs, "peak": peaks["l2_read_gbs"], "unit": "GB/s",
+        "frac": ach_gbs / peaks["l2_read_gbs"] if peaks["l2_read_gbs"] else None,
+        "traffic": None,
+        "note": "algorithmic node+sphere+hit bytes (SURVEY 8d) vs the L2 read bandwidth measured by "
+                "sahbvh_measure_peaks; node reads are L1/L2-served, HBM only sees the hit records",
+        "per_ray": alg, "kernel_ms": k_ms,
+        "fp32": {"achieved": ach_tflops, "unit": "TFLOP/s (algorithmic, 1 per non-FMA op)",
+                 "peak_mix_tinst_per_s": peaks["fp32_mix_inst_per_s"] / 1e12,
+                 "frac_of_measured_issue": ach_tflops * 1e12 / peaks["fp32_mix_inst_per_s"] if peaks["fp32_mix_inst_per_s"] else None},
+        "hbm": {"achieved": compulsory, "peak": hbm_peak, "unit": "GB/s", "frac": compulsory / hbm_peak,
+                "peak_source": peak_src, "what": "compulsory bytes: 32 B hit/ray + tree read once"},
+        "measured_peaks": peaks,
+    }
+
+    sweep = []
+    if not args.no_sweep and not dist_on:
+        sweep = run_sweep(torch, pkg, bvh, spheres, args, flush, stream, peaks)
+
+    cpu = None
+    if not dist_on and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        row_step = max(1, int(round(HEIGHT * WIDTH / (0.015e6 * threads * 15.0))))
+        try:
+            r = cpu_reference_run(args.spheres, WIDTH, HEIGHT, row_step, threads)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the checker must never take the product's number down
+            cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.spheres} random spheres (benchmark.c:306-314 recipe, srand 1), SAH BVH build(0,n,0), "
+                               f"{W}x{H} primary rays of the default camera, closest hit, 32 B hit record per ray",
+                   "rays_per_step": total_rays, "rays_per_gpu": n_local, "bvh": info, "build_seconds_host": build_s,
+                   "l2": "256 MiB device memset between timed steps (outside the per-step events)",
+                   "parallelism": f"rays sharded in {world} contiguous row band(s), BVH replicated" +
+                                  (", NCCL all_gather of the frame buffer inside the step" if dist_on else "")},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": 32 * n_local,
+                "api": "gpu_trace_primary (host output buffer, pinned); inputs are the 64-byte Camera"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "sweep": sweep,
+    }
+    print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_sweep(torch, pkg, bvh1m, spheres1m, args, flush, stream, peaks):
+    """Other single-GPU configurations of BASELINE.json, same timing method."""
+    out = []
+    cam = pkg.default_camera()
+    steps, warm = max(5, min(args.steps, 10)), 3
+
+    def one(name, bvh, fn, n_rays, stats, generated, with_input, extra=None):
+        total_ms, _ = time_steps(torch, fn, steps, warm, flush, False)
+        ms = total_ms / steps
+        alg = algorithmic(stats, generated, with_input)
+        rec = {"workload": name, "rays": n_rays, "ms_per_step": ms, "value": n_rays / (ms * 1e-3) / 1e9, "unit": UNIT,
+               "per_ray": alg,
+               "l2_frac": alg["bytes_per_ray"] * n_rays / (ms * 1e-3) / 1e9 / peaks["l2_read_gbs"] if peaks["l2_read_gbs"] else None,
+               "fp32_issue_frac": alg["flop_per_ray"] * n_rays / (ms * 1e-3) / peaks["fp32_mix_inst_per_s"] if peaks["fp32_mix_inst_per_s"] else None}
+        if extra:
+            rec.update(extra)
+        out.append(rec)
+
+    # config 2: default renderer scene, 800x600
+    pkg.srand(1)
+    s20 = pkg.random_scene(20)
+    b20 = pkg.GpuBvh.build(s20, 20, 0, 20, 0)
+    buf = torch.empty((WIDTH * HEIGHT, 8), dtype=torch.float32, device="cuda")
+    st = b20.trace_primary_stats(cam, 800, 600, 0, 600, buf.data_ptr())
+    one("default renderer scene: 20 random spheres, 800x600 primary", b20,
+        lambda: b20.trace_primary_dev(cam, 800, 600, 0, 600, buf.data_ptr(), stream), 480000, st, True, False)
+    b20.close()
+
+    # config 3: 100 K spheres, 4K primary
+    pkg.srand(1)
+    s100 = pkg.benchmark_scene(100000)
+    b100 = pkg.GpuBvh.build(s100, 100000, 0, 100000, 0)
+    st = b100.trace_primary_stats(cam, WIDTH, HEIGHT, 0, HEIGHT, buf.data_ptr())
+    one("100K random spheres, 3840x2160 primary", b100,
+        lambda: b100.trace_primary_dev(cam, WIDTH, HEIGHT, 0, HEIGHT, buf.data_ptr(), stream), WIDTH * HEIGHT, st, True, False)
+    b100.close()
+
+    # config 4: 1 M spheres, 2^24 incoherent diffuse-bounce rays (renderer.c:51-54 recipe from the 4K frame's hits)
+    n_b = 1 << 24
+    bvh1m.trace_primary_dev(cam, WIDTH, HEIGHT, 0, HEIGHT, buf.data_ptr(), stream)
+    torch.cuda.synchronize()
+    hits = buf.cpu().numpy().view(pkg.HIT_DT).reshape(-1)
+    pkg.srand(2)
+    parts, have = [], 0
+    while have < n_b:
+        r = pkg.bounce_rays(hits)
+        parts.append(r)
+        have += len(r)
+    rays = np.concatenate(parts)[:n_b]
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 6)).cuda()
+    d_hits = torch.empty((n_b, 8), dtype=torch.float32, device="cuda")
+    st = bvh1m.trace_closest_hit_stats(d_rays.data_ptr(), n_b, d_hits.data_ptr())
+    one("1M random spheres, 2^24 incoherent diffuse-bounce rays (ray buffer in HBM)", bvh1m,
+        lambda: bvh1m.trace_closest_hit_dev(d_rays.data_ptr(), n_b, d_hits.data_ptr(), stream), n_b, st, False, True)
+    # e2e of the ray-buffer API with pinned host buffers (H2D 24 B/ray + D2H 32 B/ray inside the call)
+    h_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 6)).pin_memory()
+    h_hits = torch.empty((n_b, 8), dtype=torch.float32).pin_memory()
+    bvh1m.trace_closest_hit_ptr(h_rays.data_ptr(), n_b, h_hits.data_ptr())
+    t0 = time.perf_counter()
+    for _ in range(3):
+        bvh1m.trace_closest_hit_ptr(h_rays.data_ptr(), n_b, h_hits.data_ptr())
+    dt = (time.perf_counter() - t0) / 3
+    out[-1]["e2e"] = {"value": n_b / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 24 * n_b, "d2h_bytes_per_step": 32 * n_b,
+                      "api": "gpu_trace_closest_hit (pinned host buffers)"}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

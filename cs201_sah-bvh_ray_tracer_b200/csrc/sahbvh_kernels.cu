@@ -609,6 +609,110 @@ extern "C" int gpu_trace_primary_stats(gpu_bvh *b, const Camera *cam, int width,
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* roofline denominators                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+template <bool MIX>
+__global__ void __launch_bounds__(256) k_peak_fp32(float *sink, int iters, float seed)
+{
+    float a0 = seed + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 0.001f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+            if (MIX) {
+                a4 = fminf(a4, a0); a5 = fmaxf(a5, a1); a6 = fminf(a6, a2); a7 = fmaxf(a7, a3);
+            } else {
+                a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+            }
+        }
+    }
+    float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 12345.678f) sink[0] = r;
+}
+
+__global__ void __launch_bounds__(256) k_peak_read(const float4 *__restrict__ buf, size_t n4, int repeats, float *sink)
+{
+    float acc = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < repeats; r++) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 v = __ldg(buf + i);
+            acc += v.x + v.y + v.z + v.w;
+        }
+    }
+    if (acc == 12345.678f) sink[0] = acc;
+}
+
+extern "C" int sahbvh_measure_peaks(int device, sahbvh_peaks *out)
+{
+    if (!out) return SAHBVH_E_ARG;
+    memset(out, 0, sizeof *out);
+    if (sahbvh_device_count() == 0) {
+        sahbvh_set_error("no usable CUDA device");
+        return SAHBVH_E_CUDA;
+    }
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    out->sm_count = sms;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    float *sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, 256));
+    const int blocks = sms * 8, iters = 4096;
+    float ms = 0.f;
+    for (int mix = 0; mix < 2; mix++) {
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            CU_TRY(cudaEventRecord(e0));
+            if (mix) k_peak_fp32<true><<<blocks, 256>>>(sink, iters, 1.0f);
+            else k_peak_fp32<false><<<blocks, 256>>>(sink, iters, 1.0f);
+            g_launches++;
+            CU_TRY(cudaEventRecord(e1));
+            CU_TRY(cudaEventSynchronize(e1));
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            double rate = (double)blocks * 256.0 * iters * 64.0 / (ms * 1e-3);
+            if (rep > 0 && rate > best) best = rate;
+        }
+        if (mix) out->fp32_mix_inst_per_s = best;
+        else out->ffma_inst_per_s = best;
+    }
+    for (int big = 0; big < 2; big++) {
+        size_t bytes = big ? ((size_t)2 << 30) : ((size_t)48 << 20);
+        int repeats = big ? 1 : 32;
+        float4 *buf = nullptr;
+        if (cudaMalloc(&buf, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        cudaMemset(buf, 0, bytes);
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            CU_TRY(cudaEventRecord(e0));
+            k_peak_read<<<sms * 16, 256>>>(buf, bytes / 16, repeats, sink);
+            g_launches++;
+            CU_TRY(cudaEventRecord(e1));
+            CU_TRY(cudaEventSynchronize(e1));
+            CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            double gbs = (double)bytes * repeats / (ms * 1e-3) / 1e9;
+            if (rep > 0 && gbs > best) best = gbs;
+        }
+        if (big) out->hbm_read_gbs = best;
+        else out->l2_read_gbs = best;
+        cudaFree(buf);
+    }
+    cudaFree(sink);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return SAHBVH_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* scalar drop-in backend: ray_bvh_intersect(Ray, BVHNode*) (hit.c:91)                          */
 /* ------------------------------------------------------------------------------------------ */
 

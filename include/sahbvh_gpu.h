@@ -105,6 +105,17 @@ int gpu_trace_closest_hit_stats(gpu_bvh *bvh, const void *d_rays, int64_t n, voi
 int gpu_trace_primary_stats(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
                             void *d_out, gpu_trace_stats *stats);
 
+/* Roofline denominators measured on the device in use (the L2 bandwidth and the FP32
+ * issue rate are not in MEASURED_PEAKS.json).  Micro-kernels, ~50 ms in total. */
+typedef struct sahbvh_peaks {
+    double fp32_mix_inst_per_s;  /* thread-instructions/s of an FFMA+FMNMX mix (the box-test mix), all SMs */
+    double ffma_inst_per_s;      /* thread-instructions/s of pure FFMA (x2 = FLOP/s) */
+    double l2_read_gbs;          /* float4 read sweep over a 48 MiB buffer (L2 resident) */
+    double hbm_read_gbs;         /* float4 read sweep over a 2 GiB buffer */
+    double sm_count;
+} sahbvh_peaks;
+int sahbvh_measure_peaks(int device, sahbvh_peaks *out);
+
 /* Number of kernel launches this library has issued in this process (bench.py's gpu_launches). */
 uint64_t sahbvh_kernel_launches(void);
 
