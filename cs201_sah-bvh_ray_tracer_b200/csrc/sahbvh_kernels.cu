@@ -73,7 +73,7 @@ __device__ __forceinline__ void flush_counters(const SahCounters &c, unsigned lo
 
 template <bool COUNT>
 __global__ void __launch_bounds__(TRACE_THREADS)
-k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4, int n_spheres, float r_max,
+k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
              const float *__restrict__ rays, long long n, gpu_hit *__restrict__ out, unsigned long long *counters)
 {
     int32_t stack[SAH_STACK_MAX];
@@ -83,9 +83,9 @@ k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4
     for (long long i = (long long)blockIdx.x * TRACE_THREADS + threadIdx.x; i < n; i += stride) {
         const float *rp = rays + i * 6;
         SahRay r;
-        sah_ray_setup(r, __ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3), __ldg(rp + 4), __ldg(rp + 5), r_max);
+        sah_ray_setup(r, __ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3), __ldg(rp + 4), __ldg(rp + 5), sc);
         SahHit h;
-        sah_trace_one<COUNT>(nodes, spheres4, n_spheres, r, stack, 1, h, &cnt);
+        sah_trace_one<COUNT>(nodes, spheres4, sc.n_spheres, r, stack, 1, h, &cnt);
         store_hit(out + i, h);
         if (COUNT) hits += (h.prim >= 0);
     }
@@ -94,7 +94,7 @@ k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4
 
 template <bool COUNT>
 __global__ void __launch_bounds__(PRIMARY_THREADS)
-k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spheres4, int n_spheres, float r_max,
+k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                 SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, unsigned long long *counters)
 {
     int32_t stack[SAH_STACK_MAX];
@@ -107,9 +107,9 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
         float dx, dy, dz;
         sah_primary_dir(cam, x, y, dx, dy, dz);
         SahRay r;
-        sah_ray_setup(r, cam.px, cam.py, cam.pz, dx, dy, dz, r_max);
+        sah_ray_setup(r, cam.px, cam.py, cam.pz, dx, dy, dz, sc);
         SahHit h;
-        sah_trace_one<COUNT>(nodes, spheres4, n_spheres, r, stack, 1, h, &cnt);
+        sah_trace_one<COUNT>(nodes, spheres4, sc.n_spheres, r, stack, 1, h, &cnt);
         store_hit(out + (size_t)(y - y0) * (size_t)width + (size_t)x, h);
         if (COUNT) hits += (h.prim >= 0);
     }
@@ -133,18 +133,19 @@ k_primary_rays(SahCamera cam, int width, int y0, int y1, float *__restrict__ out
 
 /* renderer.c:33-44: closest over ALL spheres, strict < so the lowest index wins ties */
 __global__ void __launch_bounds__(TRACE_THREADS)
-k_brute_force(const float *__restrict__ spheres4, int n_spheres, const float *__restrict__ rays, long long n,
+k_brute_force(const float *__restrict__ spheres4, SahScene sc, const float *__restrict__ rays, long long n,
               gpu_hit *__restrict__ out)
 {
     __shared__ float4 tile[TRACE_THREADS];
+    const int n_spheres = sc.n_spheres;
     long long i = (long long)blockIdx.x * TRACE_THREADS + threadIdx.x;
     bool live = i < n;
     SahRay r;
     if (live) {
         const float *rp = rays + i * 6;
-        sah_ray_setup(r, rp[0], rp[1], rp[2], rp[3], rp[4], rp[5], 0.0f);
+        sah_ray_setup(r, rp[0], rp[1], rp[2], rp[3], rp[4], rp[5], sc);
     } else {
-        sah_ray_setup(r, 0, 0, 0, 0, 0, 0, 0.0f);
+        sah_ray_setup(r, 0, 0, 0, 0, 0, 0, sc);
     }
     float best_t = INFINITY;
     int best = -1;
@@ -347,6 +348,19 @@ extern "C" int gpu_bvh_get_info(const gpu_bvh *b, gpu_bvh_info *info)
 /* launches                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 
+static SahScene make_scene(const gpu_bvh_info &info)
+{
+    SahScene sc;
+    sc.n_spheres = info.n_spheres;
+    sc.r_max = info.max_radius;
+    for (int a = 0; a < 3; a++) {
+        sc.lo[a] = info.scene_lo[a];
+        sc.hi[a] = info.scene_hi[a];
+    }
+    sc.geometric_zero_axes = info.empty_leaves == 0;
+    return sc;
+}
+
 static int trace_grid(const gpu_bvh *b, long long n)
 {
     long long blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;
@@ -361,10 +375,10 @@ static int launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out,
     if (n == 0) return SAHBVH_OK;
     int grid = trace_grid(b, n);
     if (count)
-        k_trace_rays<true><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+        k_trace_rays<true><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
                                                           (const float *)d_rays, n, (gpu_hit *)d_out, b->d_counters);
     else
-        k_trace_rays<false><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+        k_trace_rays<false><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
                                                            (const float *)d_rays, n, (gpu_hit *)d_out, nullptr);
     g_launches++;
     CU_TRY(cudaGetLastError());
@@ -398,10 +412,10 @@ static int launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
     make_camera(cam, width, height, &c);
     dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
     if (count)
-        k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+        k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
                                                                c, width, y0, y1, (gpu_hit *)d_out, b->d_counters);
     else
-        k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, b->info.n_spheres, b->info.max_radius,
+        k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
                                                                 c, width, y0, y1, (gpu_hit *)d_out, nullptr);
     g_launches++;
     CU_TRY(cudaGetLastError());
@@ -558,7 +572,7 @@ extern "C" int gpu_trace_brute_force(gpu_bvh *b, const Ray *rays, int64_t n, gpu
     cudaStream_t st = b->streams[0];
     CU_TRY(cudaMemcpyAsync(b->d_in[0], rays, (size_t)n * sizeof(Ray), cudaMemcpyHostToDevice, st));
     int grid = (int)((n + TRACE_THREADS - 1) / TRACE_THREADS);
-    k_brute_force<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, b->info.n_spheres, (const float *)b->d_in[0], n,
+    k_brute_force<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, make_scene(b->info), (const float *)b->d_in[0], n,
                                                  (gpu_hit *)b->d_out[0]);
     g_launches++;
     CU_TRY(cudaGetLastError());
@@ -639,7 +653,7 @@ __global__ void __launch_bounds__(256) k_peak_read(const float4 *__restrict__ bu
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (int r = 0; r < repeats; r++) {
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            float4 v = __ldg(buf + i);
+            float4 v = __ldcg(buf + i); /* L2-level load: bypass L1 so the 48 MiB sweep measures L2, not L1 */
             acc += v.x + v.y + v.z + v.w;
         }
     }

@@ -78,11 +78,20 @@ struct SahHit {  /* == gpu_hit */
 struct SahRay {
     float ox, oy, oz;
     float dx, dy, dz;
-    float ix, iy, iz;   /* 1/d, NaN on ignored axes */
-    float nx, ny, nz;   /* -(o*inv), NaN on ignored axes */
-    float a;            /* d.d in the reference's order (hit.c:22) */
-    float a2;           /* absolute slack of the conservative box test */
-    float cull_abs;     /* 2*r_max/|d| + a2 */
+    float ix, iy, iz;      /* 1/d; 2^100 on a zero/tiny axis (geometric mode); NaN on an ignored axis */
+    float nx, ny, nz;      /* addend of the LO plane: -(o*inv)            [geometric: -(o+pad)*2^100] */
+    float mx, my, mz;      /* addend of the HI plane: same as n*           [geometric: -(o-pad)*2^100] */
+    float a;               /* d.d in the reference's order (hit.c:22) */
+    float a2;              /* absolute slack of the conservative box test */
+    float cull_abs;        /* 2*r_max/|d| + a2 */
+};
+
+/* per-tree constants the ray set-up needs */
+struct SahScene {
+    int n_spheres;
+    float r_max;
+    float lo[3], hi[3];    /* bounds of all spheres */
+    int geometric_zero_axes; /* 1 unless the tree has sphere_count==0 leaves (see sah_axis_setup) */
 };
 
 struct SahCounters {
@@ -97,36 +106,71 @@ SAH_HD float sah_nan() {
 #endif
 }
 
-SAH_HD void sah_axis_setup(float o, float d, float &inv, float &neg_oi) {
-    float i = F_DIV(1.0f, d);
-    float n = -F_MUL(o, i);
-    bool ok = (fabsf(d) >= SAH_TINY_DIR) && (fabsf(n) <= 3.0e38f);
-    inv = ok ? i : sah_nan();
-    neg_oi = ok ? n : sah_nan();
+/*
+ * One axis of the conservative interior slab test:  t_lo = fma(lo, inv, n_lo), t_hi = fma(hi, inv, n_hi).
+ *
+ *  |d| >= 1e-30 : inv = 1/d, n_lo = n_hi = -(o*inv)  (see the error bound in the file header).
+ *  |d| <  1e-30 (including the reference's d == 0 rule, hit.c:54-56, which accepts EVERY box on
+ *    that axis): accepting everything makes such a ray walk the whole tree (the centre pixel of
+ *    the default camera has dx == dy == 0).  Instead the axis is tested geometrically with a pad:
+ *        accept  <=>  lo - pad <= o <= hi + pad,      inv = 2^100, n_lo = -(o+pad)*2^100, n_hi = -(o-pad)*2^100
+ *    (products by 2^100 are exact, so the signs of t_lo/t_hi are exact).  This never culls a leaf
+ *    the reference would report: with d_a == 0 the reference's float discriminant obeys
+ *    disc <= 4a(r^2 - oc_a^2) + 68u*a*|oc|^2, so a hit needs |o_a - c_a| < r + 1.0e-3*|oc|, i.e.
+ *    o_a inside the leaf's slab padded by 1.0e-3*|oc| <= pad = 2^-9 * (distance from the origin to
+ *    the farthest corner of the scene bounds).  For 0 < |d_a| < 1e-30 the reference's own leaf
+ *    test is exact containment, a subset.  The argument needs the tested sphere to lie inside
+ *    every ancestor box, which fails for sphere_count == 0 leaves (they alias a sphere owned by
+ *    another subtree): trees that contain such leaves keep the accept-everything rule.
+ *  Non-finite addends (|o| ~ 1e8 and beyond): the axis is ignored (NaN drops out of FMNMX).
+ */
+SAH_HD void sah_axis_setup(float o, float d, float pad, bool geometric, float &inv, float &n_lo, float &n_hi, float &slack_src) {
+    const float big = 1.2676506002282294e30f; /* 2^100 */
+    if (fabsf(d) >= SAH_TINY_DIR) {
+        float i = F_DIV(1.0f, d);
+        float n = -F_MUL(o, i);
+        bool ok = fabsf(n) <= 3.0e38f;
+        inv = ok ? i : sah_nan();
+        n_lo = n_hi = ok ? n : sah_nan();
+        slack_src = ok ? fabsf(n) : 0.0f;
+    } else {
+        float a = -F_MUL(F_ADD(o, pad), big), b = -F_MUL(F_SUB(o, pad), big);
+        bool ok = geometric && fabsf(a) <= 3.0e38f && fabsf(b) <= 3.0e38f;
+        inv = ok ? big : sah_nan();
+        n_lo = ok ? a : sah_nan();
+        n_hi = ok ? b : sah_nan();
+        slack_src = 0.0f;
+    }
 }
 
-SAH_HD void sah_ray_setup(SahRay &r, float ox, float oy, float oz, float dx, float dy, float dz, float r_max) {
+SAH_HD void sah_ray_setup(SahRay &r, float ox, float oy, float oz, float dx, float dy, float dz, const SahScene &sc) {
     r.ox = ox; r.oy = oy; r.oz = oz;
     r.dx = dx; r.dy = dy; r.dz = dz;
-    sah_axis_setup(ox, dx, r.ix, r.nx);
-    sah_axis_setup(oy, dy, r.iy, r.ny);
-    sah_axis_setup(oz, dz, r.iz, r.nz);
+    /* pad for geometric zero axes: 2^-9 * distance to the farthest scene corner (+ a relative crumb) */
+    float ex = fmaxf(fabsf(ox - sc.lo[0]), fabsf(ox - sc.hi[0]));
+    float ey = fmaxf(fabsf(oy - sc.lo[1]), fabsf(oy - sc.hi[1]));
+    float ez = fmaxf(fabsf(oz - sc.lo[2]), fabsf(oz - sc.hi[2]));
+    float far2 = ex * ex + ey * ey + ez * ez;
+    float pad = sqrtf(far2) * 0.001953125f + sc.r_max * 0.001953125f;
+    bool geo = sc.geometric_zero_axes != 0 && pad < 3.0e38f;
+    float sx, sy, sz;
+    sah_axis_setup(ox, dx, pad, geo, r.ix, r.nx, r.mx, sx);
+    sah_axis_setup(oy, dy, pad, geo, r.iy, r.ny, r.my, sy);
+    sah_axis_setup(oz, dz, pad, geo, r.iz, r.nz, r.mz, sz);
     r.a = F_ADD(F_ADD(F_MUL(dx, dx), F_MUL(dy, dy)), F_MUL(dz, dz));
-    float m = fmaxf(fmaxf(fabsf(r.nx), fabsf(r.ny)), fabsf(r.nz)); /* NaN operands drop out */
-    if (!(m >= 0.0f)) m = 0.0f;
-    r.a2 = m * SAH_ABS_SCALE;
+    r.a2 = fmaxf(fmaxf(sx, sy), sz) * SAH_ABS_SCALE;
     /* 2*r_max/|d|; |d| from the same float sum (exactness irrelevant: slack only) */
     float len = sqrtf(r.a);
-    float per_d = (len > 0.0f) ? (2.0f * r_max) / len : INFINITY;
+    float per_d = (len > 0.0f) ? (2.0f * sc.r_max) / len : INFINITY;
     r.cull_abs = per_d + r.a2;
 }
 
 /* conservative slab test of one box; returns entry distance through tnear */
 SAH_HD bool sah_box_conservative(const SahRay &r, float lox, float loy, float loz, float hix, float hiy, float hiz,
                                  float best_s, float &tnear) {
-    float t1x = F_FMA(lox, r.ix, r.nx), t2x = F_FMA(hix, r.ix, r.nx);
-    float t1y = F_FMA(loy, r.iy, r.ny), t2y = F_FMA(hiy, r.iy, r.ny);
-    float t1z = F_FMA(loz, r.iz, r.nz), t2z = F_FMA(hiz, r.iz, r.nz);
+    float t1x = F_FMA(lox, r.ix, r.nx), t2x = F_FMA(hix, r.ix, r.mx);
+    float t1y = F_FMA(loy, r.iy, r.ny), t2y = F_FMA(hiy, r.iy, r.my);
+    float t1z = F_FMA(loz, r.iz, r.nz), t2z = F_FMA(hiz, r.iz, r.mz);
     float tn = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
     float tf = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
     tn = fmaxf(tn, 0.0f);

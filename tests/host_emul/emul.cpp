@@ -79,10 +79,15 @@ extern "C" void emul_info(const emul_bvh *e, gpu_bvh_info *info) { *info = e->f.
 static void trace_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t hi, gpu_hit *out, SahCounters *cnt)
 {
     int32_t stack[SAH_STACK_MAX];
+    SahScene sc;
+    sc.n_spheres = e->f.info.n_spheres;
+    sc.r_max = e->f.info.max_radius;
+    for (int a = 0; a < 3; a++) { sc.lo[a] = e->f.info.scene_lo[a]; sc.hi[a] = e->f.info.scene_hi[a]; }
+    sc.geometric_zero_axes = e->f.info.empty_leaves == 0;
     for (int64_t i = lo; i < hi; i++) {
         SahRay r;
         sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
-                      rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, e->f.info.max_radius);
+                      rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, sc);
         SahHit h;
         sah_trace_one<true>(e->f.nodes, e->f.spheres4, e->f.info.n_spheres, r, stack, 1, h, cnt);
         memcpy(&out[i], &h, sizeof h);

@@ -128,7 +128,8 @@ def test_100k_primary_4k(gpu, oracle, golden, scene100k):
     r = s["r"][h["prim"]]
     assert np.all(h["t"] > 1e-6)
     assert np.allclose(np.linalg.norm(h["n"], axis=1), 1.0, atol=1e-5)
-    assert np.allclose(np.linalg.norm(h["p"] - c, axis=1), r, rtol=0, atol=0.2)   # float-noise t
+    # the reference computes the discriminant in float: t (hence the point) carries up to ~1e-3*t of noise
+    assert np.all(np.abs(np.linalg.norm(h["p"] - c, axis=1) - r) < 2e-3 * h["t"] + 0.01)
     miss = hits[hits["prim"] < 0]
     assert not miss.view(np.uint8).reshape(len(miss), 32)[:, 8:].any() and not miss["t"].any()
 
