@@ -168,11 +168,9 @@ int flat_bvh_from_tree(flat_bvh *f, const sah_tree *t, const Sphere *spheres, in
         memcpy(lo, leaf->lo, 12);
         memcpy(hi, leaf->hi, 12);
         w[0] = lo[0]; w[1] = lo[1]; w[2] = lo[2]; w[3] = hi[0];
-        w[4] = hi[1]; w[5] = hi[2]; w[6] = INFINITY; w[7] = INFINITY;
-        w[8] = INFINITY; w[9] = -INFINITY; w[10] = -INFINITY; w[11] = -INFINITY;
-        w[12] = bits_float(~leaf->sphere);
-        w[13] = bits_float(SAHBVH_REF_NONE);
-        w[14] = w[15] = 0.0f;
+        w[4] = hi[1]; w[5] = hi[2]; w[6] = bits_float(~leaf->sphere); w[7] = 0.0f;
+        w[8] = INFINITY; w[9] = INFINITY; w[10] = INFINITY; w[11] = -INFINITY;
+        w[12] = -INFINITY; w[13] = -INFINITY; w[14] = bits_float(SAHBVH_REF_NONE); w[15] = 0.0f;
     } else {
         for (int64_t i = 0; i < total; i++) {
             const sah_node *nd = &t->nodes[i];
@@ -181,15 +179,13 @@ int flat_bvh_from_tree(flat_bvh *f, const sah_tree *t, const Sphere *spheres, in
             float llo[3], lhi[3], rlo[3], rhi[3];
             child_box(t, nd, nd->left, llo, lhi);
             child_box(t, nd, nd->right, rlo, rhi);
-            w[0] = llo[0]; w[1] = llo[1]; w[2] = llo[2]; w[3] = lhi[0];
-            w[4] = lhi[1]; w[5] = lhi[2]; w[6] = rlo[0]; w[7] = rlo[1];
-            w[8] = rlo[2]; w[9] = rhi[0]; w[10] = rhi[1]; w[11] = rhi[2];
             const sah_node *l = &t->nodes[nd->left], *r = &t->nodes[nd->right];
             int32_t lref = l->sphere >= 0 ? ~l->sphere : inner_id[nd->left];
             int32_t rref = r->sphere >= 0 ? ~r->sphere : inner_id[nd->right];
-            w[12] = bits_float(lref);
-            w[13] = bits_float(rref);
-            w[14] = w[15] = 0.0f;
+            w[0] = llo[0]; w[1] = llo[1]; w[2] = llo[2]; w[3] = lhi[0];
+            w[4] = lhi[1]; w[5] = lhi[2]; w[6] = bits_float(lref); w[7] = 0.0f;
+            w[8] = rlo[0]; w[9] = rlo[1]; w[10] = rlo[2]; w[11] = rhi[0];
+            w[12] = rhi[1]; w[13] = rhi[2]; w[14] = bits_float(rref); w[15] = 0.0f;
         }
     }
     (void)float_bits;

@@ -24,11 +24,10 @@ typedef struct sah_tree {
 
 /* Flattened, device-ready form.
  *
- * Inner node = 64 bytes = 4 x 16-byte words, 64-byte aligned:
- *   w0 = { L.lo.x, L.lo.y, L.lo.z, L.hi.x }
- *   w1 = { L.hi.y, L.hi.z, R.lo.x, R.lo.y }
- *   w2 = { R.lo.z, R.hi.x, R.hi.y, R.hi.z }
- *   w3 = { left_ref, right_ref, 0, 0 }              (int32)
+ * Inner node = 64 bytes, 64-byte aligned = two 32-byte CHILD RECORDS (left, right), each
+ * two 16-byte words so that any kernel fetches a child with aligned 128-bit loads:
+ *   c0 = { lo.x, lo.y, lo.z, hi.x }
+ *   c1 = { hi.y, hi.z, ref (int32 bits), 0 }
  * child ref >= 0 : index of another inner node;  ref < 0 : leaf, sphere index = ~ref.
  * A leaf's inline box is the reference leaf's node->bounds, except for sphere_count==0
  * leaves (inverted-infinite bounds) which carry the PARENT's bounds: the reference

@@ -31,6 +31,14 @@ static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 #define PRIMARY_THREADS 256 /* 32 x 8 pixels per CTA, one 8x4 tile per warp */
 
 static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_PACKET};
+
+extern "C" int sahbvh_set_primary_mode(int mode)
+{
+    if (mode != SAHBVH_PRIMARY_PER_RAY && mode != SAHBVH_PRIMARY_PACKET) return SAHBVH_E_ARG;
+    g_primary_mode.store(mode);
+    return SAHBVH_OK;
+}
 
 #define CU_TRY(expr)                                                                              \
     do {                                                                                          \
@@ -112,6 +120,190 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
         sah_trace_one<COUNT>(nodes, spheres4, sc.n_spheres, r, stack, 1, h, &cnt);
         store_hit(out + (size_t)(y - y0) * (size_t)width + (size_t)x, h);
         if (COUNT) hits += (h.prim >= 0);
+    }
+    if (COUNT) flush_counters(cnt, hits, counters);
+}
+
+/*
+ * K2p: packet traversal for primary rays.  One WARP owns a 16x8 pixel tile (4 rays per lane,
+ * shared origin).  Interior culling is done ONCE PER TILE: the lanes test 32 child boxes of up
+ * to 16 popped nodes in parallel against the tile's direction-interval frustum
+ * (sah_frustum_box), surviving inner children are pushed back in near-last order, surviving
+ * leaves become candidates.  Every ray of the tile then runs the reference-exact sphere test
+ * (and, for a would-be winner, the reference-exact leaf box test) on each candidate, so the
+ * result is the same "best over leaves whose own tests pass" as the per-ray kernel.
+ */
+#define PKT_WARPS 4
+#define PKT_STACK 512
+#define PKT_K 4
+
+__device__ __forceinline__ float warp_min(float v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(PKT_WARPS * 32)
+k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
+                       SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, unsigned long long *counters)
+{
+    __shared__ int32_t s_stack[PKT_WARPS][PKT_STACK];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (width + 15) >> 4, tiles_y = (y1 - y0 + 7) >> 3;
+    const long long tile = (long long)blockIdx.x * PKT_WARPS + warp;
+    SahCounters cnt = {0, 0, 0, 0};
+    unsigned long long hits = 0;
+    if (tile < (long long)tiles_x * tiles_y) {
+        int32_t *stack = s_stack[warp];
+        const int tx = (int)(tile % tiles_x), ty = (int)(tile / tiles_x);
+        /* ---- this lane's 4 rays ---- */
+        float dx[PKT_K], dy[PKT_K], dz[PKT_K], ra[PKT_K], best_t[PKT_K];
+        int32_t best_p[PKT_K];
+        bool valid[PKT_K];
+        int px[PKT_K], py[PKT_K];
+        float lminx = INFINITY, lminy = INFINITY, lminz = INFINITY, lmaxx = -INFINITY, lmaxy = -INFINITY, lmaxz = -INFINITY;
+        float lmin_a = INFINITY;
+#pragma unroll
+        for (int k = 0; k < PKT_K; k++) {
+            px[k] = tx * 16 + (k & 1) * 8 + (lane & 7);
+            py[k] = y0 + ty * 8 + (k >> 1) * 4 + (lane >> 3);
+            valid[k] = px[k] < width && py[k] < y1;
+            sah_primary_dir(cam, px[k], py[k], dx[k], dy[k], dz[k]);
+            ra[k] = F_ADD(F_ADD(F_MUL(dx[k], dx[k]), F_MUL(dy[k], dy[k])), F_MUL(dz[k], dz[k]));
+            best_t[k] = 0.0f;
+            best_p[k] = -1;
+            if (valid[k]) {
+                lminx = fminf(lminx, dx[k]); lmaxx = fmaxf(lmaxx, dx[k]);
+                lminy = fminf(lminy, dy[k]); lmaxy = fmaxf(lmaxy, dy[k]);
+                lminz = fminf(lminz, dz[k]); lmaxz = fmaxf(lmaxz, dz[k]);
+                lmin_a = fminf(lmin_a, ra[k]);
+            }
+        }
+        lminx = warp_min(lminx); lminy = warp_min(lminy); lminz = warp_min(lminz);
+        lmaxx = warp_max(lmaxx); lmaxy = warp_max(lmaxy); lmaxz = warp_max(lmaxz);
+        lmin_a = warp_min(lmin_a);
+        /* ---- tile frustum (warp-uniform) ---- */
+        float ex = fmaxf(fabsf(cam.px - sc.lo[0]), fabsf(cam.px - sc.hi[0]));
+        float ey = fmaxf(fabsf(cam.py - sc.lo[1]), fabsf(cam.py - sc.hi[1]));
+        float ez = fmaxf(fabsf(cam.pz - sc.lo[2]), fabsf(cam.pz - sc.hi[2]));
+        float pad = sqrtf(ex * ex + ey * ey + ez * ez) * 0.001953125f + sc.r_max * 0.001953125f;
+        bool geo = sc.geometric_zero_axes != 0;
+        SahFrustumAxis FX, FY, FZ;
+        sah_frustum_axis_setup(FX, cam.px, lminx, lmaxx, pad, geo);
+        sah_frustum_axis_setup(FY, cam.py, lminy, lmaxy, pad, geo);
+        sah_frustum_axis_setup(FZ, cam.pz, lminz, lmaxz, pad, geo);
+        float min_len = sqrtf(lmin_a);
+        const float cull_abs = (min_len > 0.0f) ? (2.0f * sc.r_max) / min_len : INFINITY;
+        float pkt_best_s = INFINITY;
+
+        int top = 1;
+        if (lane == 0) stack[0] = 0;
+        __syncwarp();
+        while (top > 0) {
+            int npop = top < 16 ? top : 16;
+            if (top > PKT_STACK - 96) npop = 1; /* nearly full: plain DFS (growth <= tree depth) */
+            const int j = lane >> 1, c = lane & 1;
+            const bool active = j < npop;
+            int32_t nd = active ? stack[top - 1 - j] : 0;
+            __syncwarp();
+            top -= npop;
+            if (COUNT && lane == 0) cnt.inner += (unsigned long long)npop;
+            bool pass = false;
+            float tn = INFINITY, lox = 0, loy = 0, loz = 0, hix = 0, hiy = 0, hiz = 0;
+            int32_t ref = 0;
+            if (active) {
+                const float4 *rec = reinterpret_cast<const float4 *>(nodes + (size_t)nd * 16 + c * 8);
+                float4 c0 = __ldg(rec), c1 = __ldg(rec + 1);
+                lox = c0.x; loy = c0.y; loz = c0.z; hix = c0.w; hiy = c1.x; hiz = c1.y;
+                ref = __float_as_int(c1.z);
+                pass = sah_frustum_box(FX, FY, FZ, lox, loy, loz, hix, hiy, hiz, pkt_best_s, tn);
+            }
+            const bool is_leaf = ref < 0;
+            const bool push = pass && !is_leaf;
+            const bool cand = pass && is_leaf && (uint32_t)(~ref) < (uint32_t)sc.n_spheres;
+            /* stack order: children of deeper stack entries first, of the top entry last; within a pair far first */
+            float tn_other = __shfl_xor_sync(full, tn, 1);
+            int is_near = (tn < tn_other || (tn == tn_other && c == 0)) ? 1 : 0;
+            int order = (15 - j) * 2 + is_near;
+            unsigned ord_mask = __reduce_or_sync(full, push ? (1u << order) : 0u);
+            if (push) stack[top + __popc(ord_mask & ((1u << order) - 1u))] = ref;
+            top += __popc(ord_mask);
+            unsigned m = __ballot_sync(full, cand);
+            __syncwarp();
+            /* ---- candidates: every ray of the tile runs the reference's own tests ---- */
+            bool changed = false;
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int32_t sidx = ~__shfl_sync(full, ref, src);
+                const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + sidx);
+                float tt[PKT_K];
+                bool need = false, needk[PKT_K];
+#pragma unroll
+                for (int k = 0; k < PKT_K; k++) {
+                    SahRay r;
+                    r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
+                    r.dx = dx[k]; r.dy = dy[k]; r.dz = dz[k];
+                    r.a = ra[k];
+                    needk[k] = false;
+                    if (valid[k]) {
+                        if (COUNT) cnt.spheres++;
+                        if (sah_sphere_t(r, s.x, s.y, s.z, s.w, tt[k]))
+                            needk[k] = best_p[k] < 0 || tt[k] < best_t[k] || (tt[k] == best_t[k] && sidx > best_p[k]);
+                    }
+                    need |= needk[k];
+                }
+                if (__any_sync(full, need)) {
+                    const float blx = __shfl_sync(full, lox, src), bly = __shfl_sync(full, loy, src), blz = __shfl_sync(full, loz, src);
+                    const float bhx = __shfl_sync(full, hix, src), bhy = __shfl_sync(full, hiy, src), bhz = __shfl_sync(full, hiz, src);
+#pragma unroll
+                    for (int k = 0; k < PKT_K; k++) {
+                        if (needk[k]) {
+                            SahRay r;
+                            r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
+                            r.dx = dx[k]; r.dy = dy[k]; r.dz = dz[k];
+                            if (COUNT) cnt.exact++;
+                            if (sah_box_exact(r, blx, bly, blz, bhx, bhy, bhz)) {
+                                best_t[k] = tt[k];
+                                best_p[k] = sidx;
+                                changed = true;
+                            }
+                        }
+                    }
+                }
+            }
+            if (__any_sync(full, changed)) {
+                float w = 0.0f; /* worst (largest) cull bound over this lane's valid rays */
+#pragma unroll
+                for (int k = 0; k < PKT_K; k++)
+                    if (valid[k]) w = fmaxf(w, best_p[k] >= 0 ? F_FMA(best_t[k], SAH_REL_CULL, cull_abs) : INFINITY);
+                pkt_best_s = warp_max(w);
+            }
+        }
+        /* ---- results ---- */
+#pragma unroll
+        for (int k = 0; k < PKT_K; k++) {
+            if (!valid[k]) continue;
+            SahHit h;
+            if (best_p[k] >= 0) {
+                SahRay r;
+                r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
+                r.dx = dx[k]; r.dy = dy[k]; r.dz = dz[k];
+                const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + best_p[k]);
+                sah_finish_hit(r, best_t[k], best_p[k], s.x, s.y, s.z, h);
+                if (COUNT) hits++;
+            } else {
+                sah_miss(h);
+            }
+            store_hit(out + (size_t)(py[k] - y0) * (size_t)width + (size_t)px[k], h);
+        }
     }
     if (COUNT) flush_counters(cnt, hits, counters);
 }
@@ -410,13 +602,24 @@ static int launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
     if (y1 <= y0 || width <= 0) return SAHBVH_OK;
     SahCamera c;
     make_camera(cam, width, height, &c);
-    dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
-    if (count)
-        k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                               c, width, y0, y1, (gpu_hit *)d_out, b->d_counters);
-    else
-        k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                                c, width, y0, y1, (gpu_hit *)d_out, nullptr);
+    if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
+        long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + 7) / 8);
+        unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
+        if (count)
+            k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
+                                                                         c, width, y0, y1, (gpu_hit *)d_out, b->d_counters);
+        else
+            k_trace_primary_packet<false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
+                                                                          c, width, y0, y1, (gpu_hit *)d_out, nullptr);
+    } else {
+        dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
+        if (count)
+            k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
+                                                                   c, width, y0, y1, (gpu_hit *)d_out, b->d_counters);
+        else
+            k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
+                                                                    c, width, y0, y1, (gpu_hit *)d_out, nullptr);
+    }
     g_launches++;
     CU_TRY(cudaGetLastError());
     return SAHBVH_OK;

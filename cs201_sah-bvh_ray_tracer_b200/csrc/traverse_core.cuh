@@ -279,21 +279,22 @@ SAH_HD void sah_trace_one(const float *__restrict__ nodes, const float *__restri
     int32_t node = 0;
     for (;;) {
         const float *w = nodes + (size_t)node * 16;
-        SahF4 w0 = sah_ld4(w), w1 = sah_ld4(w + 4), w2 = sah_ld4(w + 8), w3 = sah_ld4(w + 12);
+        /* two 32-byte child records: {lo.xyz, hi.x} {hi.y, hi.z, ref, 0} */
+        SahF4 l0 = sah_ld4(w), l1 = sah_ld4(w + 4), r0 = sah_ld4(w + 8), r1 = sah_ld4(w + 12);
         if (COUNT) cnt->inner++;
-        int32_t lref = sah_f2i(w3.x), rref = sah_f2i(w3.y);
+        int32_t lref = sah_f2i(l1.z), rref = sah_f2i(r1.z);
         float tl, tr;
-        bool hl = sah_box_conservative(r, w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, best_s, tl);
-        bool hr = sah_box_conservative(r, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, best_s, tr);
+        bool hl = sah_box_conservative(r, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, best_s, tl);
+        bool hr = sah_box_conservative(r, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, best_s, tr);
         if (hl && lref < 0) {
-            sah_leaf<COUNT>(r, spheres4, n_spheres, lref, w0.x, w0.y, w0.z, w0.w, w1.x, w1.y,
+            sah_leaf<COUNT>(r, spheres4, n_spheres, lref, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y,
                             best_t, best_prim, best_s, cnt);
             hl = false;
         }
         if (hr && rref < 0) {
             /* re-check against a best_s the left leaf may just have tightened */
             if (tr <= best_s)
-                sah_leaf<COUNT>(r, spheres4, n_spheres, rref, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w,
+                sah_leaf<COUNT>(r, spheres4, n_spheres, rref, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y,
                                 best_t, best_prim, best_s, cnt);
             hr = false;
         }
@@ -341,6 +342,84 @@ SAH_HD void sah_primary_dir(const SahCamera &c, int x, int y, float &dx, float &
     float len = F_SQRT(F_ADD(F_ADD(F_MUL(ax, ax), F_MUL(ay, ay)), F_MUL(az, az)));
     if (len != 0.0f) { dx = F_DIV(ax, len); dy = F_DIV(ay, len); dz = F_DIV(az, len); }
     else { dx = 0.0f; dy = 0.0f; dz = 0.0f; }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Packet (shared-origin) culling: one conservative box test for ALL rays of a pixel tile.
+ *
+ * The tile's rays share the origin o and their directions lie in the per-axis intervals
+ * [dmin_a, dmax_a] (exact min/max over the tile's actual float directions).  For a box,
+ *     LB_a <= near_a(ray)   and   UB_a >= far_a(ray)    for every ray of the tile,
+ * hence  max_a LB_a > min_a UB_a  ==>  every ray has tmin > tmax  ==>  the reference's slab
+ * test (hit.c:49-82) fails for every ray: the box is culled for the whole tile.  Per axis:
+ *   all d >=  1e-30 : q/d is monotone in d, so near/far extremes sit at the interval ends:
+ *                     LB = min(qn*ia, qn*ib), UB = max(qf*ia, qf*ib), ia = 1/dmax, ib = 1/dmin,
+ *                     qn = lo - o, qf = hi - o  (the reference's own first rounding step)
+ *   all d <= -1e-30 : same with the planes swapped
+ *   straddling 0    : (may contain rays with d == 0, for which the reference accepts any slab)
+ *                     padded geometric test as in sah_axis_setup: origin inside [lo-pad, hi+pad]
+ *                     -> no constraint; below -> LB = (lo-pad-o)/dmax; above -> LB = (hi+pad-o)/dmin
+ *   mode 3          : axis ignored (trees with sphere_count==0 leaves, non-finite input)
+ * Products carry <= 2 ulp relative error against the reference's true divisions; the caller
+ * compares with a 2^-19 relative slack.
+ */
+struct SahFrustumAxis {
+    int mode;      /* 0 positive, 1 negative, 2 straddling, 3 ignored */
+    float o;
+    float ia, ib;  /* inverse-direction bounds (see above) */
+    float pad;
+};
+
+SAH_HD void sah_frustum_axis_setup(SahFrustumAxis &A, float o, float dmin, float dmax, float pad, bool geometric) {
+    A.o = o;
+    A.pad = pad;
+    A.ia = 0.0f;
+    A.ib = 0.0f;
+    if (!(dmin <= dmax) || !(fabsf(o) <= 3.0e38f)) { A.mode = 3; return; }
+    if (dmin >= SAH_TINY_DIR) {
+        A.mode = 0; A.ia = F_DIV(1.0f, dmax); A.ib = F_DIV(1.0f, dmin);
+    } else if (dmax <= -SAH_TINY_DIR) {
+        A.mode = 1; A.ia = F_DIV(1.0f, dmin); A.ib = F_DIV(1.0f, dmax);
+    } else if (geometric && pad < 3.0e38f) {
+        A.mode = 2;
+        A.ia = (dmax >= SAH_TINY_DIR) ? F_DIV(1.0f, dmax) : INFINITY;     /* fastest approach from below */
+        A.ib = (dmin <= -SAH_TINY_DIR) ? F_DIV(1.0f, dmin) : -INFINITY;   /* fastest approach from above */
+    } else {
+        A.mode = 3;
+    }
+}
+
+SAH_HD void sah_frustum_axis(const SahFrustumAxis &A, float lo, float hi, float &LB, float &UB) {
+    if (A.mode <= 1) {
+        float qn = F_SUB(A.mode == 0 ? lo : hi, A.o), qf = F_SUB(A.mode == 0 ? hi : lo, A.o);
+        LB = fminf(F_MUL(qn, A.ia), F_MUL(qn, A.ib));
+        UB = fmaxf(F_MUL(qf, A.ia), F_MUL(qf, A.ib));
+    } else if (A.mode == 2) {
+        float qlo = F_SUB(F_SUB(lo, A.pad), A.o), qhi = F_SUB(F_ADD(hi, A.pad), A.o);
+        UB = INFINITY;
+        if (qlo > 0.0f) LB = F_MUL(qlo, A.ia);
+        else if (qhi < 0.0f) LB = F_MUL(qhi, A.ib);
+        else LB = -INFINITY;
+        if (!(LB == LB)) LB = -INFINITY;   /* inf*0 cannot occur (q != 0 here); belt and braces */
+    } else {
+        LB = -INFINITY;
+        UB = INFINITY;
+    }
+}
+
+#define SAH_REL_PKT 1.0000019073486328125f /* 1 + 2^-19 */
+
+/* true if the box may be hit by some ray of the tile with entry <= best_s; tnear = packet entry bound */
+SAH_HD bool sah_frustum_box(const SahFrustumAxis &X, const SahFrustumAxis &Y, const SahFrustumAxis &Z,
+                            float lox, float loy, float loz, float hix, float hiy, float hiz, float best_s, float &tnear) {
+    float lbx, ubx, lby, uby, lbz, ubz;
+    sah_frustum_axis(X, lox, hix, lbx, ubx);
+    sah_frustum_axis(Y, loy, hiy, lby, uby);
+    sah_frustum_axis(Z, loz, hiz, lbz, ubz);
+    float tn = fmaxf(fmaxf(fmaxf(lbx, lby), lbz), 0.0f);
+    float tf = fminf(fminf(ubx, uby), ubz);
+    tnear = tn;
+    return tn <= F_FMA(tf, SAH_REL_PKT, 1e-37f) && tn <= best_s;
 }
 
 #endif /* SAHBVH_TRAVERSE_CORE_CUH */

@@ -93,6 +93,12 @@ int gpu_trace_closest_hit_dev(gpu_bvh *bvh, const void *d_rays, int64_t n, void 
 int gpu_trace_primary(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out);
 int gpu_trace_primary_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
                           void *d_out, void *stream);
+/* Which kernel gpu_trace_primary* launches (process-wide; both give identical hit records):
+ *   SAHBVH_PRIMARY_PACKET  (default) one warp per 16x8 pixel tile, interior culling once per tile
+ *   SAHBVH_PRIMARY_PER_RAY one thread per pixel, per-ray stack traversal (the ray-buffer kernel's core) */
+#define SAHBVH_PRIMARY_PER_RAY 0
+#define SAHBVH_PRIMARY_PACKET 1
+int sahbvh_set_primary_mode(int mode);
 /* Ray generation only (parity aid for ray.c): writes Ray records for rows [y0,y1). */
 int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out, int device);
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <vector>
 #include <thread>
+#include <algorithm>
 
 #include "sahbvh_internal.h"
 #include "traverse_core.cuh"
@@ -140,4 +141,126 @@ extern "C" void emul_primary_rays(const Camera *cam, int width, int height, int 
             r->origin = cam->position;
             sah_primary_dir(c, x, y, r->direction.x, r->direction.y, r->direction.z);
         }
+}
+
+/* ---- packet (tile frustum) algorithm, serial restatement of k_trace_primary_packet's logic:
+ * same frustum set-up, same conservative box test, same candidate processing and packet-wide
+ * cull bound; the warp mechanics (ballots, batch-of-16 pops) are not emulated. ---- */
+static SahScene scene_of(const emul_bvh *e)
+{
+    SahScene sc;
+    sc.n_spheres = e->f.info.n_spheres;
+    sc.r_max = e->f.info.max_radius;
+    for (int a = 0; a < 3; a++) { sc.lo[a] = e->f.info.scene_lo[a]; sc.hi[a] = e->f.info.scene_hi[a]; }
+    sc.geometric_zero_axes = e->f.info.empty_leaves == 0;
+    return sc;
+}
+
+extern "C" void emul_trace_primary_packet(const emul_bvh *e, const Camera *cam, int width, int height, int y0, int y1,
+                                          int tile_w, int tile_h, gpu_hit *out, gpu_trace_stats *stats)
+{
+    SahCamera c;
+    fill_camera(cam, width, height, &c);
+    const SahScene sc = scene_of(e);
+    const float *nodes = e->f.nodes, *spheres4 = e->f.spheres4;
+    unsigned long long inner = 0, tests = 0, exact = 0, hits = 0;
+    std::vector<int32_t> stack;
+    for (int ty = y0; ty < y1; ty += tile_h)
+        for (int tx = 0; tx < width; tx += tile_w) {
+            const int nx = std::min(tile_w, width - tx), ny = std::min(tile_h, y1 - ty), nr = nx * ny;
+            std::vector<float> dx(nr), dy(nr), dz(nr), ra(nr), bt(nr, 0.0f);
+            std::vector<int32_t> bp(nr, -1);
+            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY}, min_a = INFINITY;
+            for (int i = 0; i < nr; i++) {
+                sah_primary_dir(c, tx + i % nx, ty + i / nx, dx[i], dy[i], dz[i]);
+                ra[i] = F_ADD(F_ADD(F_MUL(dx[i], dx[i]), F_MUL(dy[i], dy[i])), F_MUL(dz[i], dz[i]));
+                mn[0] = fminf(mn[0], dx[i]); mx[0] = fmaxf(mx[0], dx[i]);
+                mn[1] = fminf(mn[1], dy[i]); mx[1] = fmaxf(mx[1], dy[i]);
+                mn[2] = fminf(mn[2], dz[i]); mx[2] = fmaxf(mx[2], dz[i]);
+                min_a = fminf(min_a, ra[i]);
+            }
+            float ex = fmaxf(fabsf(c.px - sc.lo[0]), fabsf(c.px - sc.hi[0]));
+            float ey = fmaxf(fabsf(c.py - sc.lo[1]), fabsf(c.py - sc.hi[1]));
+            float ez = fmaxf(fabsf(c.pz - sc.lo[2]), fabsf(c.pz - sc.hi[2]));
+            float pad = sqrtf(ex * ex + ey * ey + ez * ez) * 0.001953125f + sc.r_max * 0.001953125f;
+            bool geo = sc.geometric_zero_axes != 0;
+            SahFrustumAxis FX, FY, FZ;
+            sah_frustum_axis_setup(FX, c.px, mn[0], mx[0], pad, geo);
+            sah_frustum_axis_setup(FY, c.py, mn[1], mx[1], pad, geo);
+            sah_frustum_axis_setup(FZ, c.pz, mn[2], mx[2], pad, geo);
+            float min_len = sqrtf(min_a);
+            const float cull_abs = (min_len > 0.0f) ? (2.0f * sc.r_max) / min_len : INFINITY;
+            float pkt_best_s = INFINITY;
+            stack.clear();
+            stack.push_back(0);
+            while (!stack.empty()) {
+                int32_t nd = stack.back();
+                stack.pop_back();
+                inner++;
+                float tn[2];
+                bool pass[2];
+                int32_t ref[2];
+                const float *w = nodes + (size_t)nd * 16;
+                for (int ch = 0; ch < 2; ch++) {
+                    const float *q = w + ch * 8;
+                    ref[ch] = sah_f2i(q[6]);
+                    pass[ch] = sah_frustum_box(FX, FY, FZ, q[0], q[1], q[2], q[3], q[4], q[5], pkt_best_s, tn[ch]);
+                }
+                bool changed = false;
+                for (int ch = 0; ch < 2; ch++) {
+                    if (!pass[ch] || ref[ch] >= 0) continue;
+                    int32_t sidx = ~ref[ch];
+                    if ((uint32_t)sidx >= (uint32_t)sc.n_spheres) continue;
+                    const float *s = spheres4 + (size_t)sidx * 4, *q = w + ch * 8;
+                    for (int i = 0; i < nr; i++) {
+                        SahRay r;
+                        r.ox = c.px; r.oy = c.py; r.oz = c.pz;
+                        r.dx = dx[i]; r.dy = dy[i]; r.dz = dz[i];
+                        r.a = ra[i];
+                        float t;
+                        tests++;
+                        if (!sah_sphere_t(r, s[0], s[1], s[2], s[3], t)) continue;
+                        if (!(bp[i] < 0 || t < bt[i] || (t == bt[i] && sidx > bp[i]))) continue;
+                        exact++;
+                        if (!sah_box_exact(r, q[0], q[1], q[2], q[3], q[4], q[5])) continue;
+                        bt[i] = t;
+                        bp[i] = sidx;
+                        changed = true;
+                    }
+                }
+                if (changed) {
+                    float wmax = 0.0f;
+                    for (int i = 0; i < nr; i++)
+                        wmax = fmaxf(wmax, bp[i] >= 0 ? F_FMA(bt[i], SAH_REL_CULL, cull_abs) : INFINITY);
+                    pkt_best_s = wmax;
+                }
+                bool pl = pass[0] && ref[0] >= 0, pr = pass[1] && ref[1] >= 0;
+                if (pl && pr) {
+                    bool left_near = tn[0] <= tn[1];
+                    stack.push_back(left_near ? ref[1] : ref[0]);
+                    stack.push_back(left_near ? ref[0] : ref[1]);
+                } else if (pl) stack.push_back(ref[0]);
+                else if (pr) stack.push_back(ref[1]);
+            }
+            for (int i = 0; i < nr; i++) {
+                SahHit h;
+                if (bp[i] >= 0) {
+                    SahRay r;
+                    r.ox = c.px; r.oy = c.py; r.oz = c.pz;
+                    r.dx = dx[i]; r.dy = dy[i]; r.dz = dz[i];
+                    const float *s = spheres4 + (size_t)bp[i] * 4;
+                    sah_finish_hit(r, bt[i], bp[i], s[0], s[1], s[2], h);
+                    hits++;
+                } else sah_miss(h);
+                memcpy(&out[(size_t)(ty + i / nx - y0) * (size_t)width + (size_t)(tx + i % nx)], &h, sizeof h);
+            }
+        }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->rays = (uint64_t)(y1 - y0) * (uint64_t)width;
+        stats->inner_visits = inner;
+        stats->sphere_tests = tests;
+        stats->exact_box_tests = exact;
+        stats->hits = hits;
+    }
 }

@@ -346,3 +346,28 @@ def test_device_pointer_api_and_counters(gpu, oracle, emul, scene100k):
     for k in ("inner_visits", "sphere_tests", "exact_box_tests", "hits"):
         assert stats[k] == est[k], (k, stats, est)
     assert stats["max_stack"] == est["max_stack"]
+
+
+def test_packet_and_per_ray_primary_kernels_agree(gpu, oracle, scene100k):
+    """gpu_trace_primary has two kernels (one warp per 16x8 tile with tile-level culling, default;
+    one thread per pixel): identical records, also for ragged frames, bands and a moved camera."""
+    bvh, s, _, nodes = scene100k
+    cam = gpu.default_camera()
+    cam2 = cam.copy()
+    cam2["yaw"] = np.float32(-2.2)
+    cam2["pitch"] = np.float32(-0.3)
+    oracle.camera_update(cam2)
+    cam2["position"] = (10, -20, 300)
+    try:
+        for c, (w, h, y0, y1) in ((cam, (3840, 2160, 0, 2160)), (cam, (1023, 517, 0, 517)), (cam, (1023, 517, 5, 412)),
+                                  (cam2, (640, 360, 0, 360)), (cam, (17, 9, 0, 9)), (cam2, (3840, 2160, 1000, 1100))):
+            gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+            a = bvh.trace_primary(c, w, h, y0, y1)
+            gpu.set_primary_mode(gpu.PRIMARY_PER_RAY)
+            b = bvh.trace_primary(c, w, h, y0, y1)
+            assert_hits_equal(a, b, f"packet vs per-ray {w}x{h} rows [{y0},{y1})")
+            if w * (y1 - y0) <= 600000:
+                want, _ = oracle.trace_bvh(nodes, s, 100000, oracle.primary_rays(c, w, h, y0, y1))
+                assert_hits_equal(a, want, f"packet vs oracle {w}x{h}")
+    finally:
+        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
