@@ -239,11 +239,14 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if dist_on:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream().cuda_stream
+    main_stream = torch.cuda.current_stream()
+    stream = main_stream.cuda_stream
     hbm_peak, peak_src, sm_max = measured_peaks()
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush_buf = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     def flush():
         flush_buf.fill_(1)
@@ -262,50 +265,83 @@ def run_b200(args):
     rows = y1 - y0
     assert rows * world == H
     n_local = rows * W
-    frame = torch.empty((world, n_local, 8), dtype=torch.float32, device="cuda")   # all_gather target
-    my_slot = frame[rank]
+    total_rays = W * H
+    hits_local = torch.empty((n_local, 8), dtype=torch.float32, device="cuda")          # this rank's 32-byte records
+    # frame assembly (N > 1): all_gather of the compact {t, prim} ID buffer; the kernel writes this
+    # rank's band straight into its slot; double-buffered so gather k overlaps kernel k+1
+    ids = [torch.empty((world, n_local, 2), dtype=torch.float32, device="cuda") for _ in range(2)] if dist_on else None
+    comm = torch.cuda.Stream() if dist_on else None
 
-    def step():
-        bvh.trace_primary_dev(cam, W, H, y0, y1, my_slot.data_ptr(), stream)
+    def run_steps(k_steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gather_done = [None, None]
+        e0.record()
+        for k in range(k_steps):
+            flush()
+            if dist_on:
+                buf = ids[k & 1]
+                if gather_done[k & 1] is not None:
+                    main_stream.wait_event(gather_done[k & 1])
+                bvh.trace_primary_dev_ids(cam, W, H, y0, y1, hits_local.data_ptr(), buf[rank].data_ptr(), stream)
+                ek = torch.cuda.Event()
+                ek.record(main_stream)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ek)
+                    dist.all_gather_into_tensor(buf.view(world * n_local, 2), buf[rank])
+                    gd = torch.cuda.Event()
+                    gd.record(comm)
+                    gather_done[k & 1] = gd
+            else:
+                bvh.trace_primary_dev(cam, W, H, y0, y1, hits_local.data_ptr(), stream)
         if dist_on:
-            dist.all_gather_into_tensor(frame.view(-1, 8), my_slot)
+            main_stream.wait_stream(comm)
+        e1.record()
+        return e0, e1
 
+    def fence():
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run_steps(args.warmup)
+    fence()
     clocks = ClockSampler(local)
-    launches0 = pkg.kernel_launches()
-    # kernel-only duration of the dominant kernel (no collective), for the roofline
-    def kernel_only():
-        bvh.trace_primary_dev(cam, W, H, y0, y1, my_slot.data_ptr(), stream)
-
     clocks.start()
-    total_ms, per_step = time_steps(torch, step, args.steps, args.warmup, flush, dist_on)
+    launches0 = pkg.kernel_launches()
+    e0, e1 = run_steps(args.steps)
+    fence()
+    launches = pkg.kernel_launches() - launches0
     clk = clocks.stop()
-    launches = pkg.kernel_launches() - launches0 - args.warmup
-    k_ms, _ = time_steps(torch, kernel_only, max(3, min(args.steps, 10)), 1, flush, False)
-    k_ms /= max(3, min(args.steps, 10))
-
+    total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if dist_on:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    total_rays = W * H
     value = total_rays / (ms_per_step * 1e-3) / 1e9
+
+    # ---- dominant kernel alone (per-launch events, L2 flushed between launches), for the roofline
+    def kernel_only():
+        bvh.trace_primary_dev(cam, W, H, y0, y1, hits_local.data_ptr(), stream)
+
+    kn = max(3, min(args.steps, 10))
+    k_ms, _ = time_steps(torch, kernel_only, kn, 1, flush, False)
+    k_ms /= kn
 
     # ---- e2e through the host-buffer C-ABI call (pinned host output; D2H inside the timed region)
     host_out = torch.empty((n_local, 8), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        bvh.trace_primary_ptr(cam, W, H, y0, y1, host_out.data_ptr())
+        bvh.trace_primary_ptr(cam, W, H, y0, y1, host_out.data_ptr())    # returns after the last D2H chunk landed
 
     for _ in range(2):
         e2e_step()
-    torch.cuda.synchronize()
-    if dist_on:
-        dist.barrier()
+    fence()
     e2e_steps = max(3, min(args.steps, 10))
     t_e0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()        # synchronous: returns after the last D2H chunk landed
+        e2e_step()
     e2e_s = (time.perf_counter() - t_e0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist_on:
@@ -318,27 +354,43 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- work counters (instrumented kernel, untimed) -> algorithmic bytes / flops per ray
-    stats = bvh.trace_primary_stats(cam, W, H, y0, y1, my_slot.data_ptr())
-    alg = algorithmic(stats, generated=True, with_input=False)
+    # ---- work counters (instrumented kernels, untimed)
+    stats = bvh.trace_primary_stats(cam, W, H, y0, y1, hits_local.data_ptr())
+    tiles = ((W + 15) // 16) * ((rows + 7) // 8)
+    pkg.set_primary_mode(pkg.PRIMARY_PER_RAY)
+    stats_ray = bvh.trace_primary_stats(cam, W, H, y0, y1, hits_local.data_ptr())
+    pkg.set_primary_mode(pkg.PRIMARY_PACKET)
+    model = algorithmic(stats_ray, generated=True, with_input=False)      # SURVEY 8(d) per-ray figure
     peaks = pkg.measure_peaks(local)
     k_s = k_ms * 1e-3
-    ach_gbs = alg["bytes_per_ray"] * n_local / k_s / 1e9
-    ach_tflops = alg["flop_per_ray"] * n_local / k_s / 1e12
-    compulsory = (32 * n_local + info["n_inner"] * 64 + info["n_spheres"] * 16) / k_s / 1e9
+    compulsory_bytes = 32 * n_local + info["n_inner"] * 64 + (info["n_spheres"] + 1) * 16
+    touched_bytes = 64 * stats["inner_visits"] + 16 * stats["sphere_tests"] + 32 * n_local
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("k_trace_primary_packet", {}).get("dram_bytes_per_launch")
     roofline = {
-        "kernel": "k_trace_primary", "bound": "l2",
-        "achieved": ach_gbs, "peak": peaks["l2_read_gbs"], "unit": "GB/s",
-        "frac": ach_gbs / peaks["l2_read_gbs"] if peaks["l2_read_gbs"] else None,
-        "traffic": None,
-        "note": "algorithmic node+sphere+hit bytes (SURVEY 8d) vs the L2 read bandwidth measured by "
-                "sahbvh_measure_peaks; node reads are L1/L2-served, HBM only sees the hit records",
-        "per_ray": alg, "kernel_ms": k_ms,
-        "fp32": {"achieved": ach_tflops, "unit": "TFLOP/s (algorithmic, 1 per non-FMA op)",
-                 "peak_mix_tinst_per_s": peaks["fp32_mix_inst_per_s"] / 1e12,
-                 "frac_of_measured_issue": ach_tflops * 1e12 / peaks["fp32_mix_inst_per_s"] if peaks["fp32_mix_inst_per_s"] else None},
-        "hbm": {"achieved": compulsory, "peak": hbm_peak, "unit": "GB/s", "frac": compulsory / hbm_peak,
-                "peak_source": peak_src, "what": "compulsory bytes: 32 B hit/ray + tree read once"},
+        "kernel": "k_trace_primary_packet", "bound": "hbm",
+        "achieved": compulsory_bytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": compulsory_bytes / k_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": compulsory_bytes,
+        "what": "compulsory HBM bytes of one launch: 32 B hit record per ray written once + the flattened tree "
+                "(64 B/inner node, 16 B/sphere) read once; the ncu profile shows the kernel is instruction-issue bound, "
+                "not HBM bound (profiles/)",
+        "kernel_ms": k_ms,
+        "tile_work": {"tiles": tiles, "nodes_popped_per_tile": stats["inner_visits"] / tiles,
+                      "sphere_tests_per_ray": stats["sphere_tests"] / n_local,
+                      "exact_leaf_box_tests_per_ray": stats["exact_box_tests"] / n_local,
+                      "touched_bytes_per_launch": touched_bytes,
+                      "touched_gbs": touched_bytes / k_s / 1e9, "l2_read_peak_gbs": peaks["l2_read_gbs"]},
+        "survey_8d_per_ray_model": {
+            **model,
+            "equivalent_gbs": model["bytes_per_ray"] * n_local / k_s / 1e9,
+            "equivalent_tflops": model["flop_per_ray"] * n_local / k_s / 1e12,
+            "note": "bytes/flops a one-ray-per-thread traversal of the same tree performs for these rays (counted by the "
+                    "instrumented per-ray kernel); the packet kernel does this culling once per 128-ray tile, so the "
+                    "equivalent rates exceed the hardware peaks -- the gain is algorithmic"},
         "measured_peaks": peaks,
     }
 
@@ -349,7 +401,7 @@ def run_b200(args):
     cpu = None
     if not dist_on and not args.no_cpu:
         threads = os.cpu_count() or 1
-        row_step = max(1, int(round(HEIGHT * WIDTH / (0.015e6 * threads * 15.0))))
+        row_step = max(1, int(round(HEIGHT * WIDTH / (0.04e6 * threads * 15.0))))
         try:
             r = cpu_reference_run(args.spheres, WIDTH, HEIGHT, row_step, threads)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -363,12 +415,15 @@ def run_b200(args):
         "config": {"workload": f"{args.spheres} random spheres (benchmark.c:306-314 recipe, srand 1), SAH BVH build(0,n,0), "
                                f"{W}x{H} primary rays of the default camera, closest hit, 32 B hit record per ray",
                    "rays_per_step": total_rays, "rays_per_gpu": n_local, "bvh": info, "build_seconds_host": build_s,
-                   "l2": "256 MiB device memset between timed steps (outside the per-step events)",
+                   "l2": "160 MiB device memset before every timed step (inside the timed region, ~25 us)",
+                   "timing": "one CUDA-event pair around the K steps on the launch stream, max over ranks",
                    "parallelism": f"rays sharded in {world} contiguous row band(s), BVH replicated" +
-                                  (", NCCL all_gather of the frame buffer inside the step" if dist_on else "")},
+                                  (", NCCL all_gather of the {t,prim} frame ID buffer (8 B/pixel) on a side stream, "
+                                   "double-buffered so gather k overlaps kernel k+1; the kernel writes each rank's band "
+                                   "straight into its all_gather slot" if dist_on else "")},
         "clocks": clk,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 64, "d2h_bytes_per_step": 32 * n_local,
-                "api": "gpu_trace_primary (host output buffer, pinned); inputs are the 64-byte Camera"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 64 * world, "d2h_bytes_per_step": 32 * total_rays,
+                "api": "gpu_trace_primary (pinned host output buffer per rank); the only input is the 64-byte Camera"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

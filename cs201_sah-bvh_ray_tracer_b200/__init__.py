@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "gpu_bvh_upload", "gpu_bvh_build", "gpu_bvh_free", "gpu_bvh_get_info",
     "gpu_trace_closest_hit", "gpu_trace_closest_hit_dev", "gpu_trace_primary", "gpu_trace_primary_dev",
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
-    "sahbvh_measure_peaks", "sahbvh_set_primary_mode",
+    "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
@@ -257,6 +257,13 @@ class GpuBvh:
     def trace_primary_dev(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_out: int, stream: int = 0):
         _check(lib.gpu_trace_primary_dev(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
                                          C.c_void_p(d_out), C.c_void_p(stream)), "gpu_trace_primary_dev")
+
+    def trace_primary_dev_ids(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_out: int, d_ids: int,
+                              stream: int = 0):
+        """Full 32-byte records to d_out and the compact {t, prim} ID buffer to d_ids (the all-gather slot)."""
+        _check(lib.gpu_trace_primary_dev_ids(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                             C.c_void_p(d_out), C.c_void_p(d_ids), C.c_void_p(stream)),
+               "gpu_trace_primary_dev_ids")
 
     def trace_closest_hit_stats(self, d_rays: int, n: int, d_out: int) -> dict:
         st = TraceStats()

@@ -103,7 +103,8 @@ k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4
 template <bool COUNT>
 __global__ void __launch_bounds__(PRIMARY_THREADS)
 k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
-                SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, unsigned long long *counters)
+                SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
+                unsigned long long *counters)
 {
     int32_t stack[SAH_STACK_MAX];
     SahCounters cnt = {0, 0, 0, 0};
@@ -118,7 +119,9 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
         sah_ray_setup(r, cam.px, cam.py, cam.pz, dx, dy, dz, sc);
         SahHit h;
         sah_trace_one<COUNT>(nodes, spheres4, sc.n_spheres, r, stack, 1, h, &cnt);
-        store_hit(out + (size_t)(y - y0) * (size_t)width + (size_t)x, h);
+        const size_t pix = (size_t)(y - y0) * (size_t)width + (size_t)x;
+        store_hit(out + pix, h);
+        if (ids) ids[pix] = make_float2(h.t, __int_as_float(h.prim));
         if (COUNT) hits += (h.prim >= 0);
     }
     if (COUNT) flush_counters(cnt, hits, counters);
@@ -151,7 +154,8 @@ __device__ __forceinline__ float warp_max(float v)
 template <bool COUNT>
 __global__ void __launch_bounds__(PKT_WARPS * 32)
 k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
-                       SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, unsigned long long *counters)
+                       SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
+                       unsigned long long *counters)
 {
     __shared__ int32_t s_stack[PKT_WARPS][PKT_STACK];
     const unsigned full = 0xffffffffu;
@@ -302,7 +306,9 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
             } else {
                 sah_miss(h);
             }
-            store_hit(out + (size_t)(py[k] - y0) * (size_t)width + (size_t)px[k], h);
+            const size_t pix = (size_t)(py[k] - y0) * (size_t)width + (size_t)px[k];
+            store_hit(out + pix, h);
+            if (ids) ids[pix] = make_float2(h.t, __int_as_float(h.prim));
         }
     }
     if (COUNT) flush_counters(cnt, hits, counters);
@@ -597,28 +603,31 @@ static void make_camera(const Camera *cam, int width, int height, SahCamera *c)
 }
 
 static int launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
-                          cudaStream_t st, bool count)
+                          cudaStream_t st, bool count, void *d_ids = nullptr)
 {
     if (y1 <= y0 || width <= 0) return SAHBVH_OK;
     SahCamera c;
     make_camera(cam, width, height, &c);
+    gpu_hit *out = (gpu_hit *)d_out;
+    float2 *ids = (float2 *)d_ids;
+    const SahScene sc = make_scene(b->info);
     if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
         long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + 7) / 8);
         unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
         if (count)
-            k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                                         c, width, y0, y1, (gpu_hit *)d_out, b->d_counters);
+            k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
+                                                                         out, ids, b->d_counters);
         else
-            k_trace_primary_packet<false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                                          c, width, y0, y1, (gpu_hit *)d_out, nullptr);
+            k_trace_primary_packet<false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
+                                                                          out, ids, nullptr);
     } else {
         dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
         if (count)
-            k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                                   c, width, y0, y1, (gpu_hit *)d_out, b->d_counters);
+            k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
+                                                                   out, ids, b->d_counters);
         else
-            k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                                    c, width, y0, y1, (gpu_hit *)d_out, nullptr);
+            k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
+                                                                    out, ids, nullptr);
     }
     g_launches++;
     CU_TRY(cudaGetLastError());
@@ -702,6 +711,15 @@ extern "C" int gpu_trace_primary_dev(gpu_bvh *b, const Camera *cam, int width, i
     if (rc != SAHBVH_OK) return rc;
     DeviceGuard guard(b->device);
     return launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false);
+}
+
+extern "C" int gpu_trace_primary_dev_ids(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
+                                         void *d_out, void *d_ids, void *stream)
+{
+    int rc = check_frame(b, cam, width, height, y0, y1, d_out);
+    if (rc != SAHBVH_OK) return rc;
+    DeviceGuard guard(b->device);
+    return launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_ids);
 }
 
 extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out)

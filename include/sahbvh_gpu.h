@@ -93,6 +93,12 @@ int gpu_trace_closest_hit_dev(gpu_bvh *bvh, const void *d_rays, int64_t n, void 
 int gpu_trace_primary(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out);
 int gpu_trace_primary_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
                           void *d_out, void *stream);
+/* Same, and additionally writes the compact 8-byte "ID buffer" record {float t, int32 prim} per pixel
+ * to d_ids (may be NULL).  Multi-GPU frame assembly gathers THIS buffer (point and normal are pure
+ * functions of the pixel's ray, t and the replicated sphere array): the kernel writes a rank's band
+ * straight into its slot of the all-gather buffer, so no pack/copy kernel sits between them. */
+int gpu_trace_primary_dev_ids(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
+                              void *d_out, void *d_ids, void *stream);
 /* Which kernel gpu_trace_primary* launches (process-wide; both give identical hit records):
  *   SAHBVH_PRIMARY_PACKET  (default) one warp per 16x8 pixel tile, interior culling once per tile
  *   SAHBVH_PRIMARY_PER_RAY one thread per pixel, per-ray stack traversal (the ray-buffer kernel's core) */
