@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "gpu_bvh_upload", "gpu_bvh_build", "gpu_bvh_free", "gpu_bvh_get_info",
     "gpu_trace_closest_hit", "gpu_trace_closest_hit_dev", "gpu_trace_primary", "gpu_trace_primary_dev",
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
-    "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids",
+    "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
@@ -117,6 +117,13 @@ def measure_peaks(device: int = -1) -> dict:
 
 
 PRIMARY_PER_RAY, PRIMARY_PACKET = 0, 1
+
+
+RAYS_ONE_SHOT, RAYS_COOP = 0, 1
+
+
+def set_ray_mode(mode: int):
+    _check(lib.sahbvh_set_ray_mode(C.c_int(mode)), "sahbvh_set_ray_mode")
 
 
 def set_primary_mode(mode: int):

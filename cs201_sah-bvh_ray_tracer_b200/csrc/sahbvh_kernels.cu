@@ -32,6 +32,14 @@ static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_PACKET};
+static std::atomic<int> g_ray_mode{SAHBVH_RAYS_COOP};
+
+extern "C" int sahbvh_set_ray_mode(int mode)
+{
+    if (mode != SAHBVH_RAYS_ONE_SHOT && mode != SAHBVH_RAYS_COOP) return SAHBVH_E_ARG;
+    g_ray_mode.store(mode);
+    return SAHBVH_OK;
+}
 
 extern "C" int sahbvh_set_primary_mode(int mode)
 {
@@ -96,6 +104,114 @@ k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4
         sah_trace_one<COUNT>(nodes, spheres4, sc.n_spheres, r, stack, 1, h, &cnt);
         store_hit(out + i, h);
         if (COUNT) hits += (h.prim >= 0);
+    }
+    if (COUNT) flush_counters(cnt, hits, counters);
+}
+
+/*
+ * K1c: ray buffer -> hit buffer, persistent and warp-synchronous (default for gpu_trace_closest_hit*).
+ *
+ *  - cooperative node fetch: an incoherent warp visits 32 different 64-byte nodes per step.  Loaded
+ *    per lane (4 x LDG.128 at a 64-byte stride) every instruction touches 32 cache lines = 32 L1
+ *    wavefronts, 128 per step -- the measured bound of k_trace_rays on bounce rays.  Here 4 lanes
+ *    fetch the 4 x 16 bytes of ONE node in the same instruction (8 lines per instruction, 32 per
+ *    step), park them in shared memory (XOR-swizzled so both the 128-bit stores and the 128-bit
+ *    loads are bank-conflict free) and every lane reads its own node back.
+ *  - ray refill: a lane whose ray finished stores its record and takes the next ray index from the
+ *    warp's chunk (one atomicAdd per 128 rays), so lanes do not idle while the slowest ray of a warp
+ *    finishes.
+ * Per-ray arithmetic is sah_visit(), identical to the one-shot kernels.
+ */
+#define COOP_WARPS 4
+#define COOP_CHUNK 128
+
+template <bool COUNT>
+__global__ void __launch_bounds__(COOP_WARPS * 32)
+k_trace_rays_coop(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
+                  const float *__restrict__ rays, long long n, gpu_hit *__restrict__ out,
+                  unsigned long long *next_ray, unsigned long long *counters)
+{
+    __shared__ float4 s_nodes[COOP_WARPS][128];
+    int32_t stack[SAH_STACK_MAX];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *sm = s_nodes[warp];
+    const float4 *nodes4 = reinterpret_cast<const float4 *>(nodes);
+    SahCounters cnt = {0, 0, 0, 0};
+    unsigned long long hits = 0;
+
+    SahRay r;
+    sah_ray_setup(r, 0, 0, 0, 0, 0, 0, sc);
+    float best_t = 0.0f, best_s = INFINITY;
+    int32_t best_prim = -1, node = SAH_NODE_DONE;
+    int sp = 0;
+    long long ray_idx = -1;
+    long long chunk_next = 0, chunk_end = 0; /* warp-uniform */
+    bool more = true;                        /* warp-uniform: the global pool may still have rays */
+    const int c4 = lane & 3;
+
+    for (;;) {
+        unsigned idle = __ballot_sync(full, node == SAH_NODE_DONE);
+        if (idle) {
+            if (chunk_next >= chunk_end && more) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(next_ray, (unsigned long long)COOP_CHUNK);
+                base = __shfl_sync(full, base, 0);
+                if ((long long)base >= n) {
+                    more = false;
+                } else {
+                    chunk_next = (long long)base;
+                    chunk_end = (long long)base + COOP_CHUNK < n ? (long long)base + COOP_CHUNK : n;
+                }
+            }
+            const long long avail = chunk_end - chunk_next;
+            if (avail > 0) {
+                const int need = __popc(idle);
+                const int take = (long long)need < avail ? need : (int)avail;
+                const int my_rank = __popc(idle & ((1u << lane) - 1u));
+                if (node == SAH_NODE_DONE && my_rank < take) {
+                    ray_idx = chunk_next + my_rank;
+                    const float *rp = rays + ray_idx * 6;
+                    sah_ray_setup(r, __ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3), __ldg(rp + 4), __ldg(rp + 5), sc);
+                    best_t = 0.0f; best_s = INFINITY; best_prim = -1;
+                    sp = 0;
+                    node = 0;
+                }
+                chunk_next += take;
+                idle = __ballot_sync(full, node == SAH_NODE_DONE);
+            }
+            if (idle == full) {
+                if (!more && chunk_next >= chunk_end) break;
+                continue;
+            }
+        }
+        /* ---- cooperative fetch: lane L brings 16 bytes (word c4) of the node owned by lane (L>>2)+8i ---- */
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int owner = (lane >> 2) + 8 * i;
+            const int32_t onode = __shfl_sync(full, node, owner);
+            if (onode != SAH_NODE_DONE)
+                sm[c4 * 32 + (owner ^ (2 * c4))] = __ldg(nodes4 + (size_t)onode * 4 + c4);
+        }
+        __syncwarp();
+        if (node != SAH_NODE_DONE) {
+            const float4 a0 = sm[lane], a1 = sm[32 + (lane ^ 2)], b0 = sm[64 + (lane ^ 4)], b1 = sm[96 + (lane ^ 6)];
+            const SahF4 l0 = {a0.x, a0.y, a0.z, a0.w}, l1 = {a1.x, a1.y, a1.z, a1.w};
+            const SahF4 r0 = {b0.x, b0.y, b0.z, b0.w}, r1 = {b1.x, b1.y, b1.z, b1.w};
+            node = sah_visit<COUNT>(r, l0, l1, r0, r1, spheres4, sc.n_spheres, stack, 1, sp, best_t, best_prim, best_s, &cnt);
+            if (node == SAH_NODE_DONE) {
+                SahHit h;
+                if (best_prim >= 0) {
+                    const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + best_prim);
+                    sah_finish_hit(r, best_t, best_prim, s.x, s.y, s.z, h);
+                    if (COUNT) hits++;
+                } else {
+                    sah_miss(h);
+                }
+                store_hit(out + ray_idx, h);
+            }
+        }
+        __syncwarp();
     }
     if (COUNT) flush_counters(cnt, hits, counters);
 }
@@ -383,7 +499,9 @@ struct gpu_bvh {
     float *d_nodes;
     float *d_spheres4;
     uint32_t *d_colors;
-    unsigned long long *d_counters;
+    unsigned long long *d_counters; /* [0..7] work counters, [8..71] per-launch ray cursors of the persistent kernel */
+    unsigned next_counter;
+    int coop_blocks_per_sm;
     gpu_bvh_info info;
     cudaStream_t streams[2];
     /* staging for the host-buffer entry points (grown on demand) */
@@ -458,7 +576,7 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
         if ((err = cudaMalloc(&b->d_nodes, node_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_spheres4, sph_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_colors, col_bytes)) != cudaSuccess) break;
-        if ((err = cudaMalloc(&b->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) break;
+        if ((err = cudaMalloc(&b->d_counters, 72 * sizeof(unsigned long long))) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_nodes, f->nodes, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_spheres4, f->spheres4, sph_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_colors, f->colors, col_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
@@ -571,13 +689,35 @@ static int trace_grid(const gpu_bvh *b, long long n)
 static int launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count)
 {
     if (n == 0) return SAHBVH_OK;
-    int grid = trace_grid(b, n);
-    if (count)
-        k_trace_rays<true><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                          (const float *)d_rays, n, (gpu_hit *)d_out, b->d_counters);
-    else
-        k_trace_rays<false><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, make_scene(b->info),
-                                                           (const float *)d_rays, n, (gpu_hit *)d_out, nullptr);
+    const SahScene sc = make_scene(b->info);
+    if (g_ray_mode.load() == SAHBVH_RAYS_COOP) {
+        /* persistent grid: every resident warp pulls 128-ray chunks from a per-launch counter */
+        if (b->coop_blocks_per_sm == 0) {
+            int nb = 0;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_rays_coop<false>, COOP_WARPS * 32, 0));
+            b->coop_blocks_per_sm = nb > 0 ? nb : 1;
+        }
+        long long want = (n + COOP_CHUNK - 1) / COOP_CHUNK;               /* one chunk per warp at least */
+        long long blocks = (want + COOP_WARPS - 1) / COOP_WARPS;
+        long long cap = (long long)b->sm_count * b->coop_blocks_per_sm;
+        if (blocks > cap) blocks = cap;
+        unsigned long long *ctr = b->d_counters + 8 + (b->next_counter++ & 63);
+        CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+        if (count)
+            k_trace_rays_coop<true><<<(unsigned)blocks, COOP_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, (const float *)d_rays,
+                                                                                 n, (gpu_hit *)d_out, ctr, b->d_counters);
+        else
+            k_trace_rays_coop<false><<<(unsigned)blocks, COOP_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, (const float *)d_rays,
+                                                                                  n, (gpu_hit *)d_out, ctr, nullptr);
+    } else {
+        int grid = trace_grid(b, n);
+        if (count)
+            k_trace_rays<true><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc,
+                                                              (const float *)d_rays, n, (gpu_hit *)d_out, b->d_counters);
+        else
+            k_trace_rays<false><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc,
+                                                               (const float *)d_rays, n, (gpu_hit *)d_out, nullptr);
+    }
     g_launches++;
     CU_TRY(cudaGetLastError());
     return SAHBVH_OK;

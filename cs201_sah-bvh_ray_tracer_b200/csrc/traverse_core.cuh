@@ -270,6 +270,45 @@ SAH_HD void sah_leaf(const SahRay &r, const float *__restrict__ spheres4, int n_
  * One ray through the flattened tree.  `stack` is caller-provided storage of SAH_STACK_MAX ints
  * with element stride `stride` (1 for a private array, blockDim for a shared-memory column).
  */
+#define SAH_NODE_DONE (-1)
+
+/* One node visit of one ray: the node's two child records are already in registers.
+ * Returns the next inner node to visit, or SAH_NODE_DONE when the ray's stack is empty. */
+template <bool COUNT>
+SAH_HD int32_t sah_visit(const SahRay &r, const SahF4 &l0, const SahF4 &l1, const SahF4 &r0, const SahF4 &r1,
+                         const float *__restrict__ spheres4, int n_spheres, int32_t *stack, int stride, int &sp,
+                         float &best_t, int32_t &best_prim, float &best_s, SahCounters *cnt) {
+    if (COUNT) cnt->inner++;
+    int32_t lref = sah_f2i(l1.z), rref = sah_f2i(r1.z);
+    float tl, tr;
+    bool hl = sah_box_conservative(r, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, best_s, tl);
+    bool hr = sah_box_conservative(r, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, best_s, tr);
+    if (hl && lref < 0) {
+        sah_leaf<COUNT>(r, spheres4, n_spheres, lref, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y,
+                        best_t, best_prim, best_s, cnt);
+        hl = false;
+    }
+    if (hr && rref < 0) {
+        /* re-check against a best_s the left leaf may just have tightened */
+        if (tr <= best_s)
+            sah_leaf<COUNT>(r, spheres4, n_spheres, rref, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y,
+                            best_t, best_prim, best_s, cnt);
+        hr = false;
+    }
+    if (hl && hr) {
+        bool left_first = tl <= tr;
+        stack[sp * stride] = left_first ? rref : lref;
+        sp++;
+        if (COUNT && (unsigned long long)sp > cnt->max_stack) cnt->max_stack = (unsigned long long)sp;
+        return left_first ? lref : rref;
+    }
+    if (hl) return lref;
+    if (hr) return rref;
+    if (sp == 0) return SAH_NODE_DONE;
+    sp--;
+    return stack[sp * stride];
+}
+
 template <bool COUNT>
 SAH_HD void sah_trace_one(const float *__restrict__ nodes, const float *__restrict__ spheres4, int n_spheres,
                           const SahRay &r, int32_t *stack, int stride, SahHit &out, SahCounters *cnt) {
@@ -277,43 +316,11 @@ SAH_HD void sah_trace_one(const float *__restrict__ nodes, const float *__restri
     int32_t best_prim = -1;
     int sp = 0;
     int32_t node = 0;
-    for (;;) {
+    while (node != SAH_NODE_DONE) {
         const float *w = nodes + (size_t)node * 16;
         /* two 32-byte child records: {lo.xyz, hi.x} {hi.y, hi.z, ref, 0} */
         SahF4 l0 = sah_ld4(w), l1 = sah_ld4(w + 4), r0 = sah_ld4(w + 8), r1 = sah_ld4(w + 12);
-        if (COUNT) cnt->inner++;
-        int32_t lref = sah_f2i(l1.z), rref = sah_f2i(r1.z);
-        float tl, tr;
-        bool hl = sah_box_conservative(r, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, best_s, tl);
-        bool hr = sah_box_conservative(r, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, best_s, tr);
-        if (hl && lref < 0) {
-            sah_leaf<COUNT>(r, spheres4, n_spheres, lref, l0.x, l0.y, l0.z, l0.w, l1.x, l1.y,
-                            best_t, best_prim, best_s, cnt);
-            hl = false;
-        }
-        if (hr && rref < 0) {
-            /* re-check against a best_s the left leaf may just have tightened */
-            if (tr <= best_s)
-                sah_leaf<COUNT>(r, spheres4, n_spheres, rref, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y,
-                                best_t, best_prim, best_s, cnt);
-            hr = false;
-        }
-        if (hl && hr) {
-            bool left_first = tl <= tr;
-            int32_t far_ref = left_first ? rref : lref;
-            node = left_first ? lref : rref;
-            stack[sp * stride] = far_ref;
-            sp++;
-            if (COUNT && (unsigned long long)sp > cnt->max_stack) cnt->max_stack = (unsigned long long)sp;
-        } else if (hl) {
-            node = lref;
-        } else if (hr) {
-            node = rref;
-        } else {
-            if (sp == 0) break;
-            sp--;
-            node = stack[sp * stride];
-        }
+        node = sah_visit<COUNT>(r, l0, l1, r0, r1, spheres4, n_spheres, stack, stride, sp, best_t, best_prim, best_s, cnt);
     }
     if (best_prim >= 0) {
         SahF4 s = sah_ld4(spheres4 + (size_t)best_prim * 4);

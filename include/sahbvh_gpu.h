@@ -105,6 +105,12 @@ int gpu_trace_primary_dev_ids(gpu_bvh *bvh, const Camera *cam, int width, int he
 #define SAHBVH_PRIMARY_PER_RAY 0
 #define SAHBVH_PRIMARY_PACKET 1
 int sahbvh_set_primary_mode(int mode);
+/* Which kernel gpu_trace_closest_hit* launches (identical hit records):
+ *   SAHBVH_RAYS_COOP     (default) persistent warps, cooperative 4-lanes-per-node fetch, ray refill
+ *   SAHBVH_RAYS_ONE_SHOT one thread per ray, grid-stride */
+#define SAHBVH_RAYS_ONE_SHOT 0
+#define SAHBVH_RAYS_COOP 1
+int sahbvh_set_ray_mode(int mode);
 /* Ray generation only (parity aid for ray.c): writes Ray records for rows [y0,y1). */
 int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out, int device);
 

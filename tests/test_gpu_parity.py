@@ -371,3 +371,27 @@ def test_packet_and_per_ray_primary_kernels_agree(gpu, oracle, scene100k):
                 assert_hits_equal(a, want, f"packet vs oracle {w}x{h}")
     finally:
         gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+
+
+def test_ray_buffer_kernels_agree(gpu, oracle, scene100k):
+    """gpu_trace_closest_hit has two kernels (persistent cooperative-fetch with ray refill, default;
+    one-shot one thread per ray): identical records for coherent, incoherent, ragged and tiny batches."""
+    bvh, s, rays, nodes = scene100k
+    cam = gpu.default_camera()
+    h8 = bvh.trace_primary(cam, 800, 600)
+    gpu.srand(5)
+    bounce = gpu.bounce_rays(h8)
+    prim = gpu.generate_primary_rays(cam, 1023, 517)
+    try:
+        for name, batch in (("benchmark rays", rays), ("bounce", bounce), ("primary 1023x517", prim),
+                            ("ragged 1", rays[:1]), ("ragged 33", rays[:33]), ("ragged 4097", rays[:4097])):
+            gpu.set_ray_mode(gpu.RAYS_COOP)
+            a = bvh.trace_closest_hit(batch)
+            gpu.set_ray_mode(gpu.RAYS_ONE_SHOT)
+            b = bvh.trace_closest_hit(batch)
+            assert_hits_equal(a, b, f"coop vs one-shot: {name}")
+        want, _ = oracle.trace_bvh(nodes, s, 100000, bounce[:20000])
+        gpu.set_ray_mode(gpu.RAYS_COOP)
+        assert_hits_equal(bvh.trace_closest_hit(bounce[:20000]), want, "coop vs oracle (bounce)")
+    finally:
+        gpu.set_ray_mode(gpu.RAYS_COOP)
