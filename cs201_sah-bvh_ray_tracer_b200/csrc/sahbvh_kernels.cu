@@ -124,9 +124,12 @@ k_trace_rays(const float *__restrict__ nodes, const float *__restrict__ spheres4
  */
 #define COOP_WARPS 4
 #define COOP_CHUNK 128
+#ifndef COOP_MIN_BLOCKS
+#define COOP_MIN_BLOCKS 8 /* 64 registers -> 32 resident warps per SM: the kernel is latency bound on node fetches */
+#endif
 
 template <bool COUNT>
-__global__ void __launch_bounds__(COOP_WARPS * 32)
+__global__ void __launch_bounds__(COOP_WARPS * 32, COOP_MIN_BLOCKS)
 k_trace_rays_coop(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                   const float *__restrict__ rays, long long n, gpu_hit *__restrict__ out,
                   unsigned long long *next_ray, unsigned long long *counters)
