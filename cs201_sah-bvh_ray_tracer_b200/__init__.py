@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsahbvh_b200.so")
+LIB_PATH = os.environ.get("SAHBVH_LIB") or os.path.join(_HERE, "libsahbvh_b200.so")  # override: kernel-tuning builds only
 
 RAY_DT = np.dtype([("o", np.float32, 3), ("d", np.float32, 3)])                         # Ray, ray.h:5-8
 SPHERE_DT = np.dtype([("c", np.float32, 3), ("r", np.float32), ("rgba", np.uint8, 4)])   # Sphere, sphere.h:7-11
@@ -51,7 +51,7 @@ class SahBvhError(RuntimeError):
 class BvhInfo(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_spheres", C.c_int32), ("n_inner", C.c_int32),
                 ("n_leaf_refs", C.c_int32), ("max_depth", C.c_int32), ("multi_leaves", C.c_int32),
-                ("empty_leaves", C.c_int32), ("reserved", C.c_int32), ("max_radius", C.c_float),
+                ("empty_leaves", C.c_int32), ("n_wide", C.c_int32), ("max_radius", C.c_float),
                 ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3), ("device_bytes", C.c_int64)]
 
     def as_dict(self):
@@ -119,7 +119,7 @@ def measure_peaks(device: int = -1) -> dict:
 PRIMARY_PER_RAY, PRIMARY_PACKET = 0, 1
 
 
-RAYS_ONE_SHOT, RAYS_COOP = 0, 1
+RAYS_ONE_SHOT, RAYS_COOP, RAYS_WIDE = 0, 1, 2
 
 
 def set_ray_mode(mode: int):

@@ -45,6 +45,17 @@ typedef struct flat_bvh {
     gpu_bvh_info info;
 } flat_bvh;
 
+/* 4-wide, 8-bit quantised form used by the ray-buffer kernel (layout and rules: wide.c) */
+#define SAHBVH_WIDE_SPECIAL 0x40000000u
+#define SAHBVH_WIDE_STACK_MAX 192
+
+typedef struct wide_bvh {
+    uint32_t *nodes;   /* n_wide * 16 words, 64-byte aligned */
+    float *special;    /* n_special * 8 floats: lo.xyz, hi.x, hi.y, hi.z, sphere index (bits), 0 */
+    int32_t n_wide, n_special;
+    int32_t max_depth;
+} wide_bvh;
+
 void sahbvh_set_error(const char *fmt, ...);
 
 /* sah_builder.c */
@@ -57,6 +68,10 @@ BVHNode *sah_tree_to_pointers(const sah_tree *t, Sphere *spheres);
 int sah_tree_from_pointers(sah_tree *t, const BVHNode *root, const Sphere *base, int n);
 int flat_bvh_from_tree(flat_bvh *f, const sah_tree *t, const Sphere *spheres, int n);
 void flat_bvh_release(flat_bvh *f);
+
+/* wide.c */
+int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f);
+void wide_bvh_release(wide_bvh *w);
 
 /* gpu_api.cu */
 int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out);

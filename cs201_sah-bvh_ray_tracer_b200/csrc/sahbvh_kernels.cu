@@ -32,11 +32,11 @@ static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_PACKET};
-static std::atomic<int> g_ray_mode{SAHBVH_RAYS_COOP};
+static std::atomic<int> g_ray_mode{SAHBVH_RAYS_WIDE};
 
 extern "C" int sahbvh_set_ray_mode(int mode)
 {
-    if (mode != SAHBVH_RAYS_ONE_SHOT && mode != SAHBVH_RAYS_COOP) return SAHBVH_E_ARG;
+    if (mode != SAHBVH_RAYS_ONE_SHOT && mode != SAHBVH_RAYS_COOP && mode != SAHBVH_RAYS_WIDE) return SAHBVH_E_ARG;
     g_ray_mode.store(mode);
     return SAHBVH_OK;
 }
@@ -215,6 +215,137 @@ k_trace_rays_coop(const float *__restrict__ nodes, const float *__restrict__ sph
             }
         }
         __syncwarp();
+    }
+    if (COUNT) flush_counters(cnt, hits, counters);
+}
+
+/*
+ * K1w: ray buffer -> hit buffer over the 4-WIDE QUANTISED tree (default for gpu_trace_closest_hit*).
+ *
+ * Same contract as K1/K1c (leaf tests are the reference's own, see traverse_core.cuh); what changes
+ * is everything that bounded K1c in the ncu profile (profiles/r1_coop_bounce_1M_ncu_summary.txt):
+ *  - half the dependent node fetches per ray (two binary levels per 64-byte node, wide.c);
+ *  - the node is fetched by its own lane with two 256-bit loads (LDG.E.256, sm_100): 64 L1
+ *    wavefronts per warp step, the same as the 4-lanes-per-node staging through shared memory,
+ *    without its SHFL/STS/LDS instructions;
+ *  - the traversal stack lives in a bank-conflict-free shared-memory column (16 entries, overflow
+ *    in local memory): the local-memory stack of K1c missed L1 and paid an L2 round trip per pop;
+ *  - finished lanes park until WIDE_REFILL_MIN of them are idle, then store their records and
+ *    take new rays together, so the divergent finish/set-up code runs with several lanes active.
+ */
+#define WIDE_WARPS 4
+#define WIDE_CHUNK 128
+#define WIDE_FAST_STACK 16
+#ifndef WIDE_MIN_BLOCKS
+#define WIDE_MIN_BLOCKS 7
+#endif
+#ifndef WIDE_REFILL_MIN
+#define WIDE_REFILL_MIN 4
+#endif
+
+__device__ __forceinline__ void ld_wide_node(const uint32_t *__restrict__ nodes, int32_t node, uint32_t (&w)[16])
+{
+    const uint32_t *p = nodes + (size_t)node * 16;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                 : "l"(p + 8));
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(WIDE_WARPS * 32, WIDE_MIN_BLOCKS)
+k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ spheres4, const float *__restrict__ special,
+                  int n_special, SahScene sc, const float *__restrict__ rays, long long n, gpu_hit *__restrict__ out,
+                  unsigned long long *next_ray, unsigned long long *counters)
+{
+    __shared__ int32_t s_stack[WIDE_FAST_STACK][WIDE_WARPS * 32];
+    int32_t slow[SAH_WIDE_STACK_MAX - WIDE_FAST_STACK];
+    const SahStack stk = {&s_stack[0][threadIdx.x], WIDE_WARPS * 32, WIDE_FAST_STACK, slow};
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    SahCounters cnt = {0, 0, 0, 0};
+    unsigned long long hits = 0;
+
+    SahRay r;
+    sah_ray_setup(r, 0, 0, 0, 0, 0, 0, sc);
+    float best_t = 0.0f, best_s = INFINITY;
+    int32_t best_prim = -1, node = SAH_NODE_DONE;
+    int32_t pend0 = SAH_REF_NONE, pend1 = SAH_REF_NONE; /* parked leaf refs (sah_wide_visit) */
+    int stall_at = -1;                                   /* child index a stalled visit resumes from (sah_wide_visit) */
+    int sp = 0;
+    long long ray_idx = -1;                  /* >= 0: this lane owns a ray (in flight, or finished and not yet stored) */
+    long long chunk_next = 0, chunk_end = 0; /* warp-uniform */
+    bool more = true;                        /* warp-uniform: the global pool may still have rays */
+    unsigned dead = 0;                       /* warp-uniform: lanes that will get no more rays */
+    int thresh = WIDE_REFILL_MIN;            /* warp-uniform: waiting lanes that trigger a service round */
+    static_assert(SAH_NODE_DONE == -1, "lane state encoding");
+
+    for (;;) {
+        /* node >= 0: traversing; SAH_NODE_DONE (-1): no ray / finished; <= -2: stalled at node -2-node
+         * (both pending slots full).  Lanes that do not traverse wait for a service round. */
+        const unsigned act = __ballot_sync(full, node >= 0);
+        if (__popc(act | dead) <= 32 - thresh) {
+            /* ---- service round, for the whole warp at once ----
+             * 1. deferred leaf tests of every lane (also of the lanes still traversing) */
+            sah_wide_drain<COUNT>(r, spheres4, special, sc.n_spheres, n_special, pend0, pend1, best_t, best_prim, best_s, &cnt);
+            if (node < SAH_NODE_DONE) node = -2 - node;
+            /* 2. finished rays: store the record */
+            if (node == SAH_NODE_DONE && ray_idx >= 0) {
+                SahHit h;
+                if (best_prim >= 0) {
+                    const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + best_prim);
+                    sah_finish_hit(r, best_t, best_prim, s.x, s.y, s.z, h);
+                    if (COUNT) hits++;
+                } else {
+                    sah_miss(h);
+                }
+                store_hit(out + ray_idx, h);
+                ray_idx = -1;
+            }
+            /* 3. free lanes take new rays */
+            const unsigned idle = __ballot_sync(full, node == SAH_NODE_DONE);
+            if (idle && chunk_next >= chunk_end && more) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(next_ray, (unsigned long long)WIDE_CHUNK);
+                base = __shfl_sync(full, base, 0);
+                if ((long long)base >= n) {
+                    more = false;
+                } else {
+                    chunk_next = (long long)base;
+                    chunk_end = (long long)base + WIDE_CHUNK < n ? (long long)base + WIDE_CHUNK : n;
+                }
+            }
+            const long long avail = chunk_end - chunk_next;
+            if (idle && avail > 0) {
+                const int need = __popc(idle);
+                const int take = (long long)need < avail ? need : (int)avail;
+                const int my_rank = __popc(idle & ((1u << lane) - 1u));
+                if (node == SAH_NODE_DONE && my_rank < take) {
+                    ray_idx = chunk_next + my_rank;
+                    const float *rp = rays + ray_idx * 6;
+                    sah_ray_setup(r, __ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3), __ldg(rp + 4), __ldg(rp + 5), sc);
+                    sah_ray_to_wide(r);
+                    best_t = 0.0f; best_s = INFINITY; best_prim = -1;
+                    sp = 0;
+                    node = 0;
+                }
+                chunk_next += take;
+            }
+            if (!more && chunk_next >= chunk_end) {
+                /* pool exhausted: lanes without a ray are out; flush every finished ray at once */
+                dead = __ballot_sync(full, node == SAH_NODE_DONE);
+                thresh = 1;
+                if (dead == full) break;
+            }
+        }
+        if (node >= 0) {
+            uint32_t w[16];
+            ld_wide_node(nodes, node, w);
+            node = sah_wide_visit<COUNT>(r, w, node, stk, sp, best_s, pend0, pend1, stall_at, &cnt);
+            if (stall_at >= 0) node = -2 - node;
+        }
     }
     if (COUNT) flush_counters(cnt, hits, counters);
 }
@@ -502,6 +633,10 @@ struct gpu_bvh {
     float *d_nodes;
     float *d_spheres4;
     uint32_t *d_colors;
+    uint32_t *d_wide;   /* 4-wide quantised nodes (wide.c), 64 B each */
+    float *d_special;   /* special-leaf records, 32 B each */
+    int n_wide, n_special;
+    int wide_blocks_per_sm;
     unsigned long long *d_counters; /* [0..7] work counters, [8..71] per-launch ray cursors of the persistent kernel */
     unsigned next_counter;
     int coop_blocks_per_sm;
@@ -571,6 +706,16 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
     b->device = device;
     b->info = f->info;
     b->info.device = device;
+    wide_bvh wb;
+    int wrc = wide_bvh_from_flat(&wb, f);
+    if (wrc != SAHBVH_OK) {
+        free(b);
+        return wrc;
+    }
+    b->n_wide = wb.n_wide;
+    b->n_special = wb.n_special;
+    b->info.n_wide = wb.n_wide;
+    const size_t wide_bytes = (size_t)wb.n_wide * 64, special_bytes = (size_t)(wb.n_special > 0 ? wb.n_special : 1) * 32;
     size_t node_bytes = (size_t)f->info.n_inner * 64;
     size_t sph_bytes = ((size_t)f->info.n_spheres + 1) * 16;
     size_t col_bytes = ((size_t)f->info.n_spheres + 1) * 4;
@@ -580,6 +725,10 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
         if ((err = cudaMalloc(&b->d_spheres4, sph_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_colors, col_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_counters, 72 * sizeof(unsigned long long))) != cudaSuccess) break;
+        if ((err = cudaMalloc(&b->d_wide, wide_bytes)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&b->d_special, special_bytes)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(b->d_wide, wb.nodes, wide_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(b->d_special, wb.special, special_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_nodes, f->nodes, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_spheres4, f->spheres4, sph_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_colors, f->colors, col_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
@@ -587,12 +736,13 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
         if ((err = cudaStreamCreateWithFlags(&b->streams[1], cudaStreamNonBlocking)) != cudaSuccess) break;
         if ((err = cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) break;
     } while (0);
+    wide_bvh_release(&wb);
     if (err != cudaSuccess) {
         sahbvh_set_error("gpu_bvh upload failed: %s", cudaGetErrorString(err));
         gpu_bvh_free(b);
         return SAHBVH_E_CUDA;
     }
-    b->info.device_bytes = (int64_t)(node_bytes + sph_bytes + col_bytes);
+    b->info.device_bytes = (int64_t)(node_bytes + sph_bytes + col_bytes + wide_bytes + special_bytes);
     *out = b;
     return SAHBVH_OK;
 }
@@ -650,6 +800,8 @@ extern "C" void gpu_bvh_free(gpu_bvh *b)
     if (b->d_spheres4) cudaFree(b->d_spheres4);
     if (b->d_colors) cudaFree(b->d_colors);
     if (b->d_counters) cudaFree(b->d_counters);
+    if (b->d_wide) cudaFree(b->d_wide);
+    if (b->d_special) cudaFree(b->d_special);
     free(b);
 }
 
@@ -693,7 +845,26 @@ static int launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out,
 {
     if (n == 0) return SAHBVH_OK;
     const SahScene sc = make_scene(b->info);
-    if (g_ray_mode.load() == SAHBVH_RAYS_COOP) {
+    if (g_ray_mode.load() == SAHBVH_RAYS_WIDE) {
+        /* persistent grid over the 4-wide tree: every resident warp pulls 128-ray chunks */
+        if (b->wide_blocks_per_sm == 0) {
+            int nb = 0;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_rays_wide<false>, WIDE_WARPS * 32, 0));
+            b->wide_blocks_per_sm = nb > 0 ? nb : 1;
+        }
+        long long want = (n + WIDE_CHUNK - 1) / WIDE_CHUNK;
+        long long blocks = (want + WIDE_WARPS - 1) / WIDE_WARPS;
+        long long cap = (long long)b->sm_count * b->wide_blocks_per_sm;
+        if (blocks > cap) blocks = cap;
+        unsigned long long *ctr = b->d_counters + 8 + (b->next_counter++ & 63);
+        CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+        if (count)
+            k_trace_rays_wide<true><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->d_spheres4, b->d_special, b->n_special, sc,
+                                                                                 (const float *)d_rays, n, (gpu_hit *)d_out, ctr, b->d_counters);
+        else
+            k_trace_rays_wide<false><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->d_spheres4, b->d_special, b->n_special, sc,
+                                                                                  (const float *)d_rays, n, (gpu_hit *)d_out, ctr, nullptr);
+    } else if (g_ray_mode.load() == SAHBVH_RAYS_COOP) {
         /* persistent grid: every resident warp pulls 128-ray chunks from a per-launch counter */
         if (b->coop_blocks_per_sm == 0) {
             int nb = 0;

@@ -29,6 +29,9 @@
 
 #include <math.h>
 #include <stdint.h>
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 #if defined(__CUDACC__)
 #define SAH_HD __host__ __device__ __forceinline__
@@ -329,6 +332,269 @@ SAH_HD void sah_trace_one(const float *__restrict__ nodes, const float *__restri
         sah_miss(out);
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * 4-wide quantised nodes (layout and containment guarantee: wide.c).
+ *
+ * Decoded plane of byte q:  p + (1024 + q) * s   (p, s from the node; s a power of two).
+ * Per node and axis:   s_inv = s * inv                 exact (power of two)
+ *                      A_lo  = fma(p, inv, n_lo),  A_hi = fma(p, inv, n_hi)
+ * per child plane:     t     = fma(1024 + q, s_inv, A)  1024 + q exact in fp16 and fp32
+ * Against the true t of the DECODED plane the error is
+ *     <= 4u|t| + u|o*inv|          (as for sah_box_conservative: covered by SAH_REL_BOX and a2)
+ *      + u|A| + u|(1024+q)*s_inv|  (the intermediate A can be as large as |t| + 1279|s_inv|)
+ *     <= ... + 2^-13 |s_inv|,
+ * i.e. 2^-13 of a grid cell in t-space; the decoded box contains the true child box with a
+ * margin of 2^-9 cell on every side, so a box the reference accepts is never rejected.  Zero /
+ * tiny direction axes use the geometric mode of sah_axis_setup unchanged (inv = 2^100 > 0, two
+ * addends); an axis whose p is NaN (not quantisable) yields NaN planes, which drop out of
+ * FMNMX: the axis accepts everything.
+ * The near/far plane of an axis is picked by the sign of inv once per node (monotone rounding
+ * keeps t_near <= t_far for qlo <= qhi), which is equivalent to the min/max form.
+ * --------------------------------------------------------------------------------------------- */
+#if defined(__CUDA_ARCH__)
+#define SAH_UNROLL _Pragma("unroll")
+#else
+#define SAH_UNROLL
+#endif
+#define SAH_WIDE_SPECIAL 0x40000000u
+#define SAH_WIDE_STACK_MAX 192
+#define SAH_KEY_NONE 0xffffffffu
+
+/* traversal stack: the first `fast_depth` entries in `fast` (element stride `stride`: a private
+ * array on the host, a bank-conflict-free shared-memory column on the device), overflow in `slow` */
+struct SahStack {
+    int32_t *fast;
+    int stride;
+    int fast_depth;
+    int32_t *slow;
+};
+SAH_HD void sah_push(const SahStack &k, int &sp, int32_t v) {
+    if (sp < k.fast_depth) k.fast[sp * k.stride] = v;
+    else k.slow[sp - k.fast_depth] = v;
+    sp++;
+}
+SAH_HD int32_t sah_pop(const SahStack &k, int &sp) {
+    sp--;
+    return sp < k.fast_depth ? k.fast[sp * k.stride] : k.slow[sp - k.fast_depth];
+}
+
+#if defined(__CUDA_ARCH__)
+SAH_HD float sah_u2f(uint32_t u) { return __uint_as_float(u); }
+SAH_HD uint32_t sah_f2u(float f) { return __float_as_uint(f); }
+#else
+SAH_HD float sah_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+SAH_HD uint32_t sah_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+#endif
+/* the four bytes of w as floats 1024 + b.  Device: two PRMTs build the fp16 pairs 0x64bb
+ * (= 1024 + b exactly) and HADD2.F32 widens them on the FMA pipe -- I2F.U8 runs on the
+ * quarter-rate XU pipe, which the ncu profile showed as a co-bottleneck of the wide kernel. */
+#if defined(__CUDA_ARCH__)
+SAH_HD void sah_bytes1024(uint32_t w, float (&f)[4]) {
+    const uint32_t lo = __byte_perm(w, 0x64646464u, 0x4140), hi = __byte_perm(w, 0x64646464u, 0x4342);
+    const __half2 hl = *reinterpret_cast<const __half2 *>(&lo), hh = *reinterpret_cast<const __half2 *>(&hi);
+    f[0] = __low2float(hl); f[1] = __high2float(hl); f[2] = __low2float(hh); f[3] = __high2float(hh);
+}
+#else
+SAH_HD void sah_bytes1024(uint32_t w, float (&f)[4]) {
+    for (int k = 0; k < 4; k++) f[k] = 1024.0f + (float)((w >> (8 * k)) & 0xffu);
+}
+#endif
+
+/* leaf of a wide node: regular (box recomputed from the sphere, bvh.c:26-35) or special (table) */
+template <bool COUNT>
+SAH_HD void sah_wide_leaf(const SahRay &r, const float *__restrict__ spheres4, const float *__restrict__ special,
+                          int n_spheres, int n_special, int32_t ref,
+                          float &best_t, int32_t &best_prim, float &best_s, SahCounters *cnt) {
+    const uint32_t code = (uint32_t)~ref;
+    int32_t idx;
+    float lox, loy, loz, hix, hiy, hiz;
+    SahF4 s;
+    if (code & SAH_WIDE_SPECIAL) {
+        const uint32_t k = code & ~SAH_WIDE_SPECIAL;
+        if (k >= (uint32_t)n_special) return;
+        const SahF4 a = sah_ld4(special + (size_t)k * 8), b = sah_ld4(special + (size_t)k * 8 + 4);
+        idx = sah_f2i(b.z);
+        if ((uint32_t)idx >= (uint32_t)n_spheres) return;
+        lox = a.x; loy = a.y; loz = a.z; hix = a.w; hiy = b.x; hiz = b.y;
+        s = sah_ld4(spheres4 + (size_t)idx * 4);
+    } else {
+        idx = (int32_t)code;
+        if ((uint32_t)idx >= (uint32_t)n_spheres) return;
+        s = sah_ld4(spheres4 + (size_t)idx * 4);
+        lox = F_SUB(s.x, s.w); loy = F_SUB(s.y, s.w); loz = F_SUB(s.z, s.w);
+        hix = F_ADD(s.x, s.w); hiy = F_ADD(s.y, s.w); hiz = F_ADD(s.z, s.w);
+    }
+    if (COUNT) cnt->spheres++;
+    float t;
+    if (!sah_sphere_t(r, s.x, s.y, s.z, s.w, t)) return;
+    const bool better = (best_prim < 0) || (t < best_t) || (t == best_t && idx > best_prim);
+    if (!better) return;
+    if (COUNT) cnt->exact++;
+    if (!sah_box_exact(r, lox, loy, loz, hix, hiy, hiz)) return;
+    best_t = t;
+    best_prim = idx;
+    best_s = F_FMA(t, SAH_REL_CULL, r.cull_abs);
+}
+
+#define SAH_CE(ka, ra, kb, rb)                                   \
+    do {                                                         \
+        const bool sw_ = (kb) < (ka);                            \
+        const uint32_t k0_ = sw_ ? (kb) : (ka), k1_ = sw_ ? (ka) : (kb); \
+        const int32_t r0_ = sw_ ? (rb) : (ra), r1_ = sw_ ? (ra) : (rb);  \
+        (ka) = k0_; (kb) = k1_; (ra) = r0_; (rb) = r1_;          \
+    } while (0)
+
+/* Put a ray set up by sah_ray_setup into "wide form": n* becomes the addend of the NEAR plane of
+ * its axis and m* the addend of the FAR plane (they differ only on geometric zero axes, where
+ * inv = 2^100 > 0 and near = lo already).  sah_wide_visit expects this form. */
+SAH_HD void sah_ray_to_wide(SahRay &r) {
+    if (!(r.ix >= 0.0f)) { const float t = r.nx; r.nx = r.mx; r.mx = t; }
+    if (!(r.iy >= 0.0f)) { const float t = r.ny; r.ny = r.my; r.my = t; }
+    if (!(r.iz >= 0.0f)) { const float t = r.nz; r.nz = r.mz; r.mz = t; }
+}
+
+/* One wide-node visit of one ray (in wide form); w[] = the 16 words of node `self`.  Returns the
+ * next wide node or SAH_NODE_DONE when the ray's stack is empty.
+ *
+ * Leaf children that pass the box test are NOT tested here: their refs are parked in the ray's two
+ * pending slots (pend0/pend1, SAH_REF_NONE = free) and the caller runs sah_wide_leaf on them
+ * later, for many rays at once (a warp runs the divergent sphere code with several lanes active
+ * instead of one).  Deferral is safe because the result is a best-over-leaves: it only delays the
+ * tightening of best_s.  If both slots are taken when leaf child c needs one, the visit sets
+ * stall_at = c and returns `self` unchanged; the caller drains the slots and repeats the visit,
+ * which then parks only children >= c (so a node with 3 or 4 hit leaves makes progress).
+ * stall_at is -1 on entry and exit otherwise. */
+template <bool COUNT>
+SAH_HD int32_t sah_wide_visit(const SahRay &r, const uint32_t (&w)[16], int32_t self, const SahStack &stk, int &sp,
+                              float best_s, int32_t &pend0, int32_t &pend1, int &stall_at, SahCounters *cnt) {
+    const float sx = F_MUL(sah_u2f(w[3]), r.ix), sy = F_MUL(sah_u2f(w[14]), r.iy), sz = F_MUL(sah_u2f(w[15]), r.iz);
+    const float px = sah_u2f(w[0]), py = sah_u2f(w[1]), pz = sah_u2f(w[2]);
+    const float anx = F_FMA(px, r.ix, r.nx), afx = F_FMA(px, r.ix, r.mx);
+    const float any_ = F_FMA(py, r.iy, r.ny), afy = F_FMA(py, r.iy, r.my);
+    const float anz = F_FMA(pz, r.iz, r.nz), afz = F_FMA(pz, r.iz, r.mz);
+    const bool posx = r.ix >= 0.0f, posy = r.iy >= 0.0f, posz = r.iz >= 0.0f;
+    const uint32_t qnx = posx ? w[4] : w[7], qfx = posx ? w[7] : w[4];
+    const uint32_t qny = posy ? w[5] : w[8], qfy = posy ? w[8] : w[5];
+    const uint32_t qnz = posz ? w[6] : w[9], qfz = posz ? w[9] : w[6];
+
+    float fnx[4], ffx[4], fny[4], ffy[4], fnz[4], ffz[4];
+    sah_bytes1024(qnx, fnx); sah_bytes1024(qfx, ffx);
+    sah_bytes1024(qny, fny); sah_bytes1024(qfy, ffy);
+    sah_bytes1024(qnz, fnz); sah_bytes1024(qfz, ffz);
+    float tn[4];
+    bool hit[4];
+    int32_t ref[4];
+    int32_t leaf_bits = 0; /* sign bit set <=> some hit child is a leaf */
+SAH_UNROLL
+    for (int c = 0; c < 4; c++) {
+        ref[c] = (int32_t)w[10 + c];
+        const float tnx = F_FMA(fnx[c], sx, anx), tfx = F_FMA(ffx[c], sx, afx);
+        const float tny = F_FMA(fny[c], sy, any_), tfy = F_FMA(ffy[c], sy, afy);
+        const float tnz = F_FMA(fnz[c], sz, anz), tfz = F_FMA(ffz[c], sz, afz);
+        tn[c] = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.0f);
+        const float f_ = fminf(F_FMA(fminf(fminf(tfx, tfy), tfz), SAH_REL_BOX, r.a2), best_s);
+        /* an absent child (SAH_REF_NONE, inverted grid box) can pass only when every axis is
+         * ignored; it then looks like a special leaf with an out-of-range index and is skipped */
+        hit[c] = tn[c] <= f_;
+        leaf_bits |= hit[c] ? ref[c] : 0;
+    }
+    const int from = stall_at;
+    stall_at = -1;
+    if (leaf_bits < 0) {
+        int over = -1;
+SAH_UNROLL
+        for (int c = 0; c < 4; c++)
+            if (hit[c] && ref[c] < 0 && c >= from && over < 0) {
+                if (pend0 == SAH_REF_NONE) pend0 = ref[c];
+                else if (pend1 == SAH_REF_NONE) pend1 = ref[c];
+                else over = c;
+            }
+        stall_at = over;
+        if (over >= 0) return self;
+    }
+    if (COUNT) cnt->inner++;
+    /* inner children, nearest first; ties by slot */
+    uint32_t k0, k1, k2, k3;
+    {
+        uint32_t k[4];
+SAH_UNROLL
+        for (int c = 0; c < 4; c++)
+            k[c] = (hit[c] && ref[c] >= 0) ? ((sah_f2u(tn[c]) & 0x7ffffffcu) + (uint32_t)c) : SAH_KEY_NONE;
+        k0 = k[0]; k1 = k[1]; k2 = k[2]; k3 = k[3];
+    }
+    int32_t r0 = ref[0], r1 = ref[1], r2 = ref[2], r3 = ref[3];
+    SAH_CE(k0, r0, k1, r1);
+    SAH_CE(k2, r2, k3, r3);
+    SAH_CE(k0, r0, k2, r2);   /* k0 = nearest */
+    SAH_CE(k1, r1, k3, r3);   /* k3 = farthest; k1, k2 stay in slot-pair order (only matters with 3+ hits) */
+    if (k0 == SAH_KEY_NONE) {
+        if (sp == 0) return SAH_NODE_DONE;
+        return sah_pop(stk, sp);
+    }
+    if (sp + 3 <= stk.fast_depth) {
+        /* common case, branch free: the up to three farther children go to sp.. in far-to-near
+         * order; a slot written for an absent child is overwritten by the next store or push */
+        int32_t *top = stk.fast + sp * stk.stride;
+        int a = (k3 != SAH_KEY_NONE) ? 1 : 0;
+        top[0] = r3;
+        top[a * stk.stride] = r2;
+        a += (k2 != SAH_KEY_NONE) ? 1 : 0;
+        top[a * stk.stride] = r1;
+        a += (k1 != SAH_KEY_NONE) ? 1 : 0;
+        sp += a;
+    } else {
+        if (k3 != SAH_KEY_NONE) sah_push(stk, sp, r3);
+        if (k2 != SAH_KEY_NONE) sah_push(stk, sp, r2);
+        if (k1 != SAH_KEY_NONE) sah_push(stk, sp, r1);
+    }
+    if (COUNT && (unsigned long long)sp > cnt->max_stack) cnt->max_stack = (unsigned long long)sp;
+    return r0;
+}
+
+/* run the deferred leaf tests of one ray and free its pending slots */
+template <bool COUNT>
+SAH_HD void sah_wide_drain(const SahRay &r, const float *__restrict__ spheres4, const float *__restrict__ special,
+                           int n_spheres, int n_special, int32_t &pend0, int32_t &pend1,
+                           float &best_t, int32_t &best_prim, float &best_s, SahCounters *cnt) {
+    if (pend0 != SAH_REF_NONE) sah_wide_leaf<COUNT>(r, spheres4, special, n_spheres, n_special, pend0, best_t, best_prim, best_s, cnt);
+    if (pend1 != SAH_REF_NONE) sah_wide_leaf<COUNT>(r, spheres4, special, n_spheres, n_special, pend1, best_t, best_prim, best_s, cnt);
+    pend0 = SAH_REF_NONE;
+    pend1 = SAH_REF_NONE;
+}
+
+#if !defined(__CUDA_ARCH__)
+/* host-side loop over sah_wide_visit (tests/host_emul only; the device loop lives in the kernel).
+ * `drain_every` = how many visits may pass before the pending leaves are tested: 1 tests them
+ * right away, larger values exercise the deferral (and the stall path) the kernel relies on. */
+template <bool COUNT>
+SAH_HD void sah_wide_trace_one(const uint32_t *nodes, const float *spheres4, const float *special,
+                               int n_spheres, int n_special, const SahRay &r, const SahStack &stk, int drain_every,
+                               SahHit &out, SahCounters *cnt) {
+    float best_t = 0.0f, best_s = INFINITY;
+    int32_t best_prim = -1;
+    int sp = 0;
+    int32_t node = 0, pend0 = SAH_REF_NONE, pend1 = SAH_REF_NONE;
+    int stall_at = -1;
+    SahRay rw = r;
+    sah_ray_to_wide(rw);
+    long long step = 0;
+    while (node != SAH_NODE_DONE) {
+        uint32_t w[16];
+        memcpy(w, nodes + (size_t)node * 16, 64);
+        node = sah_wide_visit<COUNT>(rw, w, node, stk, sp, best_s, pend0, pend1, stall_at, cnt);
+        if (stall_at >= 0 || ++step % drain_every == 0)
+            sah_wide_drain<COUNT>(rw, spheres4, special, n_spheres, n_special, pend0, pend1, best_t, best_prim, best_s, cnt);
+    }
+    sah_wide_drain<COUNT>(rw, spheres4, special, n_spheres, n_special, pend0, pend1, best_t, best_prim, best_s, cnt);
+    if (best_prim >= 0) {
+        SahF4 s = sah_ld4(spheres4 + (size_t)best_prim * 4);
+        sah_finish_hit(r, best_t, best_prim, s.x, s.y, s.z, out);
+    } else {
+        sah_miss(out);
+    }
+}
+#endif
 
 /* primary-ray constants computed once on the host (ray.c:18-24) */
 struct SahCamera {

@@ -1,0 +1,257 @@
+/*
+ * wide.c -- binary flattened tree (flatten.c) -> 4-wide, 8-bit quantised, 64-byte nodes.
+ *
+ * Why: an incoherent ray fetches one node per step from a different cache line than its warp
+ * neighbours, so the ray-buffer kernel is bound by dependent L2 round trips and by L1 wavefronts
+ * per step (ncu, profiles/).  Folding two binary levels into one 64-byte node halves the steps at
+ * the same bytes per step.  This is legal because interior boxes only cull (the
+ * reference result = best over LEAVES whose own exact box + sphere tests pass), so interior
+ * boxes may be replaced by any boxes that CONTAIN them.  Leaves keep their exact box:
+ *   regular leaf  (box bit-identical to {c - r, c + r}, bvh.c:26-35; every sphere_count==1 leaf):
+ *                 ref = ~sphere_index, the kernel recomputes the box from the float4 sphere;
+ *   special leaf  (sphere_count > 1 (Q2), sphere_count == 0 (Q3, carries its parent's box), or a
+ *                 foreign tree whose leaf box is not the sphere box): ref = ~(SPECIAL | k) into a
+ *                 table of 32-byte records {lo.xyz, hi.x, hi.y, hi.z, sphere index, 0};
+ *   leaves that can never report a hit (sphere index == n: the reference's one-past-the-end
+ *                 read, defined here as a miss; absent sibling of a synthetic root) are dropped.
+ *
+ * Node layout (16 x uint32, 64-byte aligned):
+ *   w0..w2   p.xyz  (float)  origin of the node's quantisation grid; NaN = axis not quantisable,
+ *                            the axis then accepts everything (NaN drops out of FMNMX)
+ *   w3       s.x  (float)  grid cell size of the x axis, an exact power of two (s.y, s.z: w14, w15)
+ *   w4..w6   qlo_x, qlo_y, qlo_z   one byte per child (child c in bits 8c..8c+7)
+ *   w7..w9   qhi_x, qhi_y, qhi_z
+ *   w10..w13 ref[4]  >= 0 wide node index; < 0 leaf (see above); SAHBVH_REF_NONE = no child
+ *   w14,w15  s.y, s.z
+ * Decoded plane of byte q = p + (1024 + q)*s (the kernel widens the bytes through fp16 1024 + q,
+ * see sah_bytes1024), and, in exact arithmetic,
+ *   p + (1024 + qlo)*s <= lo - s/512   and   p + (1024 + qhi)*s >= hi + s/512
+ * (checked here per child and axis in long double; an axis that fails the check is marked
+ * not quantisable).  The s/512 margin absorbs the rounding of the kernel's two FMAs per plane
+ * (<= 2^-15 s, see traverse_core.cuh), so no run-time widening is needed.
+ *
+ * Children are chosen by the usual surface-area greedy collapse: start from the two children of
+ * a binary node and repeatedly open the inner child with the largest area until there are 4.
+ */
+#include "sahbvh_internal.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float lo[3], hi[3]; int32_t ref; } rec_t;
+
+typedef struct {
+    const flat_bvh *f;
+    wide_bvh *w;
+    int64_t cap_nodes, cap_special;
+    int rc;
+    int max_depth;
+} ctx_t;
+
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static void load_rec(const flat_bvh *f, int32_t node, int child, rec_t *r)
+{
+    const float *q = f->nodes + (size_t)node * 16 + child * 8;
+    r->lo[0] = q[0]; r->lo[1] = q[1]; r->lo[2] = q[2];
+    r->hi[0] = q[3]; r->hi[1] = q[4]; r->hi[2] = q[5];
+    r->ref = (int32_t)f2u(q[6]);
+}
+
+static float rec_area(const rec_t *r)
+{
+    float dx = r->hi[0] - r->lo[0], dy = r->hi[1] - r->lo[1], dz = r->hi[2] - r->lo[2];
+    float a = dx * dy + dy * dz + dz * dx;
+    return a == a ? a : INFINITY; /* NaN boxes are opened first */
+}
+
+/* leaf record -> wide leaf ref (or SAHBVH_REF_NONE when it can never hit) */
+static int32_t leaf_ref(ctx_t *c, const rec_t *r)
+{
+    const flat_bvh *f = c->f;
+    int32_t idx = ~r->ref;
+    if (r->ref == SAHBVH_REF_NONE || (uint32_t)idx >= (uint32_t)f->info.n_spheres) return SAHBVH_REF_NONE;
+    const float *s = f->spheres4 + (size_t)idx * 4;
+    float lo[3] = {s[0] - s[3], s[1] - s[3], s[2] - s[3]}, hi[3] = {s[0] + s[3], s[1] + s[3], s[2] + s[3]};
+    if (memcmp(lo, r->lo, 12) == 0 && memcmp(hi, r->hi, 12) == 0) return ~idx;
+    wide_bvh *w = c->w;
+    if (w->n_special == c->cap_special) {
+        int64_t ncap = c->cap_special ? c->cap_special * 2 : 1024;
+        float *ns = (float *)realloc(w->special, (size_t)ncap * 32);
+        if (!ns) { c->rc = SAHBVH_E_NOMEM; return SAHBVH_REF_NONE; }
+        w->special = ns;
+        c->cap_special = ncap;
+    }
+    float *q = w->special + (size_t)w->n_special * 8;
+    q[0] = r->lo[0]; q[1] = r->lo[1]; q[2] = r->lo[2]; q[3] = r->hi[0];
+    q[4] = r->hi[1]; q[5] = r->hi[2]; q[6] = u2f((uint32_t)idx); q[7] = 0.0f;
+    return ~(int32_t)(SAHBVH_WIDE_SPECIAL | (uint32_t)w->n_special++);
+}
+
+/* quantise one axis of up to 4 child boxes; returns 0 and fills p/e/qlo/qhi, or -1 (axis ignored) */
+static int quantise_axis(const rec_t *ch, int n, int a, float *p_out, int *e_out, uint8_t qlo[4], uint8_t qhi[4])
+{
+    double mn = INFINITY, mx = -INFINITY, maxabs = 0.0;
+    for (int k = 0; k < n; k++) {
+        double lo = ch[k].lo[a], hi = ch[k].hi[a];
+        if (!isfinite(lo) || !isfinite(hi) || lo > hi) return -1;
+        if (lo < mn) mn = lo;
+        if (hi > mx) mx = hi;
+        if (fabs(lo) > maxabs) maxabs = fabs(lo);
+        if (fabs(hi) > maxabs) maxabs = fabs(hi);
+    }
+    if (n == 0) return -1;
+    double ext = mx - mn;
+    /* smallest grid with 253 cells >= extent, but never finer than 8 ulp of the coordinates
+     * (p is a float: its own rounding must stay well inside one cell) */
+    int e = -60;
+    if (ext > 0.0) {
+        int ee;
+        frexp(ext / 253.0, &ee); /* ext/253 = m * 2^ee, m in [0.5,1) -> 2^ee >= ext/253 */
+        if (ee > e) e = ee;
+    }
+    if (maxabs > 0.0) {
+        int ea;
+        frexp(maxabs, &ea);      /* maxabs < 2^ea, ulp(float) <= 2^(ea-24) */
+        if (ea - 24 + 3 > e) e = ea - 24 + 3;
+    }
+    if (e > 27) return -1;
+    double s = ldexp(1.0, e);
+    float p = (float)(mn - 1024.5 * s);
+    while ((double)p > mn - 1024.25 * s) p = nextafterf(p, -INFINITY);
+    if (!isfinite(p)) return -1;
+    for (int k = 0; k < n; k++) {
+        double l = floor(((double)ch[k].lo[a] - (double)p) / s - 1024.0 - 1.0 / 256.0);
+        double h = ceil(((double)ch[k].hi[a] - (double)p) / s - 1024.0 + 1.0 / 256.0);
+        if (l < 0.0 || h > 255.0) return -1;
+        /* containment with margin s/512, in long double */
+        long double dl = (long double)p + (1024.0L + (long double)l) * (long double)s;
+        long double dh = (long double)p + (1024.0L + (long double)h) * (long double)s;
+        long double m = (long double)s / 512.0L;
+        if (!(dl <= (long double)ch[k].lo[a] - m) || !(dh >= (long double)ch[k].hi[a] + m)) return -1;
+        qlo[k] = (uint8_t)l;
+        qhi[k] = (uint8_t)h;
+    }
+    *p_out = p;
+    *e_out = e;
+    return 0;
+}
+
+static int32_t emit(ctx_t *c, int32_t b2, int depth)
+{
+    wide_bvh *w = c->w;
+    if (c->rc != SAHBVH_OK) return SAHBVH_REF_NONE;
+    if (w->n_wide == c->cap_nodes) {
+        int64_t ncap = c->cap_nodes * 2;
+        uint32_t *nn = (uint32_t *)aligned_alloc(64, (size_t)ncap * 64);
+        if (!nn) { c->rc = SAHBVH_E_NOMEM; return SAHBVH_REF_NONE; }
+        memcpy(nn, w->nodes, (size_t)w->n_wide * 64);
+        free(w->nodes);
+        w->nodes = nn;
+        c->cap_nodes = ncap;
+    }
+    const int32_t me = w->n_wide++;
+    if (depth > c->max_depth) c->max_depth = depth;
+
+    rec_t ch[4];
+    int n = 2;
+    load_rec(c->f, b2, 0, &ch[0]);
+    load_rec(c->f, b2, 1, &ch[1]);
+    while (n < 4) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int k = 0; k < n; k++)
+            if (ch[k].ref >= 0) {
+                float a = rec_area(&ch[k]);
+                if (a > best_area) { best_area = a; best = k; }
+            }
+        if (best < 0) break;
+        int32_t open = ch[best].ref;
+        for (int k = n; k > best + 1; k--) ch[k] = ch[k - 1]; /* keep left-to-right order */
+        load_rec(c->f, open, 0, &ch[best]);
+        load_rec(c->f, open, 1, &ch[best + 1]);
+        n++;
+    }
+    /* resolve leaf refs, drop children that can never hit */
+    int m = 0;
+    for (int k = 0; k < n; k++) {
+        if (ch[k].ref < 0) {
+            int32_t lr = leaf_ref(c, &ch[k]);
+            if (lr == SAHBVH_REF_NONE) continue;
+            ch[k].ref = lr;
+        }
+        ch[m++] = ch[k];
+    }
+    n = m;
+
+    uint32_t node[16];
+    memset(node, 0, sizeof node);
+    static const int s_word[3] = {3, 14, 15};
+    for (int a = 0; a < 3; a++) {
+        float p = NAN;
+        int e = 0;
+        uint8_t qlo[4] = {255, 255, 255, 255}, qhi[4] = {0, 0, 0, 0};
+        if (quantise_axis(ch, n, a, &p, &e, qlo, qhi) != 0) {
+            p = NAN;
+            e = 0;
+        }
+        node[a] = f2u(p);
+        node[s_word[a]] = f2u(ldexpf(1.0f, e));
+        for (int k = 0; k < 4; k++) {
+            node[4 + a] |= (uint32_t)(k < n ? qlo[k] : 255) << (8 * k);
+            node[7 + a] |= (uint32_t)(k < n ? qhi[k] : 0) << (8 * k);
+        }
+    }
+    for (int k = 0; k < 4; k++) node[10 + k] = (uint32_t)SAHBVH_REF_NONE;
+    for (int k = 0; k < n; k++) {
+        int32_t ref = ch[k].ref;
+        if (ref >= 0) ref = emit(c, ref, depth + 1); /* may reallocate w->nodes */
+        node[10 + k] = (uint32_t)ref;
+    }
+    memcpy(c->w->nodes + (size_t)me * 16, node, 64);
+    return me;
+}
+
+int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f)
+{
+    memset(w, 0, sizeof *w);
+    if (!f || !f->nodes || f->info.n_inner <= 0) {
+        sahbvh_set_error("wide: empty tree");
+        return SAHBVH_E_ARG;
+    }
+    ctx_t c;
+    memset(&c, 0, sizeof c);
+    c.f = f;
+    c.w = w;
+    c.cap_nodes = (int64_t)f->info.n_inner / 2 + 16;
+    c.rc = SAHBVH_OK;
+    w->nodes = (uint32_t *)aligned_alloc(64, (size_t)c.cap_nodes * 64);
+    if (!w->nodes) return SAHBVH_E_NOMEM;
+    emit(&c, 0, 0);
+    if (c.rc != SAHBVH_OK) {
+        wide_bvh_release(w);
+        return c.rc;
+    }
+    if (3 * (c.max_depth + 1) + 4 > SAHBVH_WIDE_STACK_MAX) {
+        sahbvh_set_error("wide: tree depth %d exceeds the traversal stack", c.max_depth);
+        wide_bvh_release(w);
+        return SAHBVH_E_DEPTH;
+    }
+    w->max_depth = c.max_depth;
+    if (!w->special) { /* keep a valid pointer for the upload */
+        w->special = (float *)calloc(8, sizeof(float));
+        if (!w->special) { wide_bvh_release(w); return SAHBVH_E_NOMEM; }
+    }
+    return SAHBVH_OK;
+}
+
+void wide_bvh_release(wide_bvh *w)
+{
+    free(w->nodes);
+    free(w->special);
+    w->nodes = NULL;
+    w->special = NULL;
+    w->n_wide = w->n_special = 0;
+}

@@ -46,7 +46,7 @@ typedef struct gpu_bvh_info {
     int32_t max_depth;       /* levels below the root */
     int32_t multi_leaves;    /* leaves with sphere_count > 1 (Q2) */
     int32_t empty_leaves;    /* leaves with sphere_count == 0 (Q3) */
-    int32_t reserved;
+    int32_t n_wide;          /* 64-byte nodes of the 4-wide quantised tree (ray-buffer kernel) */
     float max_radius;
     float scene_lo[3], scene_hi[3];
     int64_t device_bytes;
@@ -106,10 +106,13 @@ int gpu_trace_primary_dev_ids(gpu_bvh *bvh, const Camera *cam, int width, int he
 #define SAHBVH_PRIMARY_PACKET 1
 int sahbvh_set_primary_mode(int mode);
 /* Which kernel gpu_trace_closest_hit* launches (identical hit records):
- *   SAHBVH_RAYS_COOP     (default) persistent warps, cooperative 4-lanes-per-node fetch, ray refill
- *   SAHBVH_RAYS_ONE_SHOT one thread per ray, grid-stride */
+ *   SAHBVH_RAYS_WIDE     (default) persistent warps over the 4-wide, 8-bit quantised tree (64-byte
+ *                        nodes, two binary levels per fetch), shared-memory stack, batched ray refill
+ *   SAHBVH_RAYS_COOP     persistent warps over the binary tree, cooperative 4-lanes-per-node fetch
+ *   SAHBVH_RAYS_ONE_SHOT one thread per ray over the binary tree, grid-stride */
 #define SAHBVH_RAYS_ONE_SHOT 0
 #define SAHBVH_RAYS_COOP 1
+#define SAHBVH_RAYS_WIDE 2
 int sahbvh_set_ray_mode(int mode);
 /* Ray generation only (parity aid for ray.c): writes Ray records for rows [y0,y1). */
 int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out, int device);

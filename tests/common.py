@@ -37,11 +37,13 @@ def assert_hits_equal(got, want, what=""):
 class HostEmul:
     """tests/host_emul/libsahbvh_host_emul.so: csrc/traverse_core.cuh compiled for the host (test-only)."""
 
-    def __init__(self):
+    def __init__(self, tree="binary"):
+        self.tree = tree   # "binary": 64-byte binary nodes (sah_trace_one); "wide": 4-wide quantised nodes (sah_wide_trace_one)
         so = os.path.join(ROOT, "tests", "host_emul", "libsahbvh_host_emul.so")
         srcs = [os.path.join(ROOT, "tests", "host_emul", "emul.cpp"),
                 os.path.join(PKG_DIR, "csrc", "traverse_core.cuh"),
                 os.path.join(PKG_DIR, "csrc", "flatten.c"),
+                os.path.join(PKG_DIR, "csrc", "wide.c"),
                 os.path.join(PKG_DIR, "csrc", "sah_builder.c"),
                 os.path.join(PKG_DIR, "csrc", "host_ref_api.c")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
@@ -71,11 +73,28 @@ class HostEmul:
     def free(self, h):
         self.lib.emul_free(C.c_void_p(h))
 
-    def trace(self, h, rays, threads=8):
+    def wide_info(self, h):
+        out = (C.c_int32 * 3)()
+        assert self.lib.emul_wide_info(C.c_void_p(h), out) == 0
+        return {"n_wide": out[0], "n_special": out[1], "max_depth": out[2]}
+
+    def wide_arrays(self, h):
+        info = self.wide_info(h)
+        nodes = np.zeros((info["n_wide"], 16), np.uint32)
+        special = np.zeros((max(info["n_special"], 1), 8), np.float32)
+        assert self.lib.emul_wide_copy(C.c_void_p(h), _ptr(nodes), _ptr(special)) == 0
+        return nodes, special[:info["n_special"]]
+
+    def trace(self, h, rays, threads=8, tree=None, fast_depth=16, drain_every=7):
         rays = np.ascontiguousarray(rays)
         hits = np.zeros(len(rays), HIT_DT)
         st = (C.c_uint64 * 6)()
-        self.lib.emul_trace(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), _ptr(hits), st, C.c_int(threads))
+        if (tree or self.tree) == "wide":
+            rc = self.lib.emul_wide_trace(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), _ptr(hits), st, C.c_int(threads),
+                                          C.c_int(fast_depth), C.c_int(drain_every))
+            assert rc == 0
+        else:
+            self.lib.emul_trace(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), _ptr(hits), st, C.c_int(threads))
         stats = dict(zip(("rays", "inner_visits", "sphere_tests", "exact_box_tests", "hits", "max_stack"), map(int, st)))
         return hits, stats
 

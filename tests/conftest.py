@@ -39,10 +39,12 @@ def pkg():
     return g.load_pkg()
 
 
-@pytest.fixture(scope="session")
-def emul():
+@pytest.fixture(scope="session", params=["binary", "wide"])
+def emul(request):
+    """Host build of the traversal core over the binary flattened tree and over the 4-wide
+    quantised tree (csrc/wide.c): every host-logic test runs against both."""
     from common import HostEmul
-    return HostEmul()
+    return HostEmul(request.param)
 
 
 @pytest.fixture(scope="session")

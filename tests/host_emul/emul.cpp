@@ -26,6 +26,8 @@ extern "C" void sahbvh_scalar_forget(const BVHNode *) {}
 
 struct emul_bvh {
     flat_bvh f;
+    wide_bvh w;   /* built lazily by emul_wide_* */
+    bool has_wide;
 };
 
 static emul_bvh *wrap(sah_tree *t, const Sphere *spheres, int n, int rc)
@@ -72,6 +74,7 @@ extern "C" void emul_free(emul_bvh *e)
 {
     if (!e) return;
     flat_bvh_release(&e->f);
+    if (e->has_wide) wide_bvh_release(&e->w);
     free(e);
 }
 
@@ -263,4 +266,74 @@ extern "C" void emul_trace_primary_packet(const emul_bvh *e, const Camera *cam, 
         stats->exact_box_tests = exact;
         stats->hits = hits;
     }
+}
+
+/* ---- 4-wide quantised tree (csrc/wide.c) + sah_wide_visit, the arithmetic of k_trace_rays_wide ---- */
+static int ensure_wide(emul_bvh *e)
+{
+    if (e->has_wide) return SAHBVH_OK;
+    int rc = wide_bvh_from_flat(&e->w, &e->f);
+    e->has_wide = rc == SAHBVH_OK;
+    return rc;
+}
+
+extern "C" int emul_wide_info(emul_bvh *e, int32_t *out3)
+{
+    int rc = ensure_wide(e);
+    if (rc != SAHBVH_OK) return rc;
+    out3[0] = e->w.n_wide;
+    out3[1] = e->w.n_special;
+    out3[2] = e->w.max_depth;
+    return SAHBVH_OK;
+}
+
+extern "C" int emul_wide_copy(emul_bvh *e, uint32_t *nodes, float *special)
+{
+    int rc = ensure_wide(e);
+    if (rc != SAHBVH_OK) return rc;
+    memcpy(nodes, e->w.nodes, (size_t)e->w.n_wide * 64);
+    if (e->w.n_special) memcpy(special, e->w.special, (size_t)e->w.n_special * 32);
+    return SAHBVH_OK;
+}
+
+static void wide_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t hi, gpu_hit *out, SahCounters *cnt, int fast_depth,
+                       int drain_every)
+{
+    int32_t fast[SAH_WIDE_STACK_MAX], slow[SAH_WIDE_STACK_MAX];
+    const SahStack stk = {fast, 1, fast_depth, slow};
+    const SahScene sc = scene_of(e);
+    for (int64_t i = lo; i < hi; i++) {
+        SahRay r;
+        sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
+                      rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, sc);
+        SahHit h;
+        sah_wide_trace_one<true>(e->w.nodes, e->f.spheres4, e->w.special, e->f.info.n_spheres, e->w.n_special, r, stk, drain_every, h, cnt);
+        memcpy(&out[i], &h, sizeof h);
+    }
+}
+
+extern "C" int emul_wide_trace(emul_bvh *e, const Ray *rays, int64_t n, gpu_hit *out, gpu_trace_stats *stats, int threads,
+                               int fast_depth, int drain_every)
+{
+    int rc = ensure_wide(e);
+    if (rc != SAHBVH_OK) return rc;
+    if (threads < 1) threads = 1;
+    std::vector<SahCounters> cnt((size_t)threads, SahCounters{0, 0, 0, 0});
+    std::vector<std::thread> pool;
+    for (int k = 0; k < threads; k++)
+        pool.emplace_back(wide_range, e, rays, n * k / threads, n * (k + 1) / threads, out, &cnt[(size_t)k], fast_depth,
+                          drain_every < 1 ? 1 : drain_every);
+    for (auto &t : pool) t.join();
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->rays = (uint64_t)n;
+        for (auto &c : cnt) {
+            stats->inner_visits += c.inner;
+            stats->sphere_tests += c.spheres;
+            stats->exact_box_tests += c.exact;
+            if (c.max_stack > stats->max_stack) stats->max_stack = c.max_stack;
+        }
+        for (int64_t i = 0; i < n; i++) stats->hits += out[i].prim >= 0;
+    }
+    return SAHBVH_OK;
 }

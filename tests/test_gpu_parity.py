@@ -335,17 +335,31 @@ def test_device_pointer_api_and_counters(gpu, oracle, emul, scene100k):
     got = d_hits.cpu().numpy().view(HIT_DT).reshape(-1)
     want = bvh.trace_closest_hit(sub)
     assert_hits_equal(got, want, "device-pointer API")
-    stats = bvh.trace_closest_hit_stats(d_rays.data_ptr(), len(sub), d_hits.data_ptr())
-    assert_hits_equal(d_hits.cpu().numpy().view(HIT_DT).reshape(-1), want, "instrumented kernel")
-    # the same traversal core compiled for the host must count the same work
     oracle.srand(1)
     sp = oracle.scene_benchmark(100000)
     h = emul.build(sp, 100000, 0, 100000, 0)
-    _, est = emul.trace(h, sub)
-    emul.free(h)
-    for k in ("inner_visits", "sphere_tests", "exact_box_tests", "hits"):
-        assert stats[k] == est[k], (k, stats, est)
-    assert stats["max_stack"] == est["max_stack"]
+    try:
+        # binary tree, one thread per ray: the same traversal core compiled for the host counts the same work
+        gpu.set_ray_mode(gpu.RAYS_ONE_SHOT)
+        stats = bvh.trace_closest_hit_stats(d_rays.data_ptr(), len(sub), d_hits.data_ptr())
+        assert_hits_equal(d_hits.cpu().numpy().view(HIT_DT).reshape(-1), want, "instrumented kernel (binary)")
+        _, est = emul.trace(h, sub, tree="binary")
+        for k in ("inner_visits", "sphere_tests", "exact_box_tests", "hits"):
+            assert stats[k] == est[k], (k, stats, est)
+        assert stats["max_stack"] == est["max_stack"]
+        # 4-wide tree: the kernel defers leaf tests to warp-wide service rounds, so its node count sits
+        # between the host loop that tests leaves at once and the one that defers them to the very end
+        gpu.set_ray_mode(gpu.RAYS_WIDE)
+        stats = bvh.trace_closest_hit_stats(d_rays.data_ptr(), len(sub), d_hits.data_ptr())
+        assert_hits_equal(d_hits.cpu().numpy().view(HIT_DT).reshape(-1), want, "instrumented kernel (wide)")
+        _, lo = emul.trace(h, sub, tree="wide", drain_every=1)
+        _, hi = emul.trace(h, sub, tree="wide", drain_every=1 << 30)
+        assert stats["hits"] == lo["hits"]
+        assert lo["inner_visits"] <= stats["inner_visits"] <= hi["inner_visits"], (lo, stats, hi)
+        assert stats["inner_visits"] < 0.6 * est["inner_visits"]     # two binary levels per fetch
+    finally:
+        gpu.set_ray_mode(gpu.RAYS_WIDE)
+        emul.free(h)
 
 
 def test_packet_and_per_ray_primary_kernels_agree(gpu, oracle, scene100k):
@@ -374,8 +388,9 @@ def test_packet_and_per_ray_primary_kernels_agree(gpu, oracle, scene100k):
 
 
 def test_ray_buffer_kernels_agree(gpu, oracle, scene100k):
-    """gpu_trace_closest_hit has two kernels (persistent cooperative-fetch with ray refill, default;
-    one-shot one thread per ray): identical records for coherent, incoherent, ragged and tiny batches."""
+    """gpu_trace_closest_hit has three kernels (persistent over the 4-wide quantised tree, default;
+    persistent cooperative-fetch over the binary tree; one-shot one thread per ray): identical
+    records for coherent, incoherent, ragged and tiny batches."""
     bvh, s, rays, nodes = scene100k
     cam = gpu.default_camera()
     h8 = bvh.trace_primary(cam, 800, 600)
@@ -390,8 +405,63 @@ def test_ray_buffer_kernels_agree(gpu, oracle, scene100k):
             gpu.set_ray_mode(gpu.RAYS_ONE_SHOT)
             b = bvh.trace_closest_hit(batch)
             assert_hits_equal(a, b, f"coop vs one-shot: {name}")
+            gpu.set_ray_mode(gpu.RAYS_WIDE)
+            c = bvh.trace_closest_hit(batch)
+            assert_hits_equal(c, b, f"wide vs one-shot: {name}")
         want, _ = oracle.trace_bvh(nodes, s, 100000, bounce[:20000])
-        gpu.set_ray_mode(gpu.RAYS_COOP)
-        assert_hits_equal(bvh.trace_closest_hit(bounce[:20000]), want, "coop vs oracle (bounce)")
+        for mode in (gpu.RAYS_COOP, gpu.RAYS_WIDE):
+            gpu.set_ray_mode(mode)
+            assert_hits_equal(bvh.trace_closest_hit(bounce[:20000]), want, f"mode {mode} vs oracle (bounce)")
     finally:
-        gpu.set_ray_mode(gpu.RAYS_COOP)
+        gpu.set_ray_mode(gpu.RAYS_WIDE)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_ray_buffer_kernels_on_degenerate_trees(gpu, oracle, golden, mode):
+    """Every ray-buffer kernel on the trees with special leaves: empty leaves (seeds 649/1164, Q3),
+    depth-40 multi-sphere leaves (5000 varying radii, Q2; benchmark.c's depth-20 build) and coincident
+    spheres (ties, nodes whose four children are all hit leaves)."""
+    answers, _ = golden
+    cam = gpu.default_camera()
+    try:
+        gpu.set_ray_mode(mode)
+        for seed in (649, 1164):
+            gpu.srand(seed)
+            s = gpu.random_scene(20)
+            bvh = gpu.GpuBvh.build(s, 20, 0, 20, 0)
+            rays = gpu.generate_primary_rays(cam, 800, 600)
+            assert sha(bvh.trace_closest_hit(rays)) == answers["cases"][f"default_seed{seed}"]["sha_hits"]
+            bvh.close()
+        case = answers["cases"]["random5000_seed3"]
+        gpu.srand(3)
+        s = gpu.random_scene(5000)
+        bvh = gpu.GpuBvh.build(s, 5000, 0, 5000, 0)
+        rays = gpu.generate_primary_rays(cam, 800, 600)[::7].copy()
+        assert sha(bvh.trace_closest_hit(rays)) == case["sha_hits"]
+        bvh.close()
+        # benchmark.c:317 as shipped at 200 K: depth0 = 20 leaves multi-sphere leaves behind (SURVEY Q2)
+        oracle.srand(1)
+        so = oracle.scene_benchmark(200000)
+        s = so.copy()
+        nodes = oracle.build(so, 0, 199999, 20)
+        bvh = gpu.GpuBvh.build(s, 200000, 0, 199999, 20)
+        assert same(s, so) and bvh.info()["multi_leaves"] > 0
+        rays = oracle.rays_benchmark(30000)
+        want, _ = oracle.trace_bvh(nodes, so, 200000, rays)
+        assert_hits_equal(bvh.trace_closest_hit(rays), want, "200K as shipped")
+        bvh.close()
+        s = np.zeros(13, SPHERE_DT)
+        s["c"][:12] = (0, 0, -10)
+        s["r"][:12] = 1.0
+        s["c"][4:8] = (0.25, 0, -10)
+        so = s.copy()
+        nodes = oracle.build(so, 0, 12, 0)
+        bvh = gpu.GpuBvh.build(s, 12, 0, 12, 0)
+        rays = np.zeros(64, RAY_DT)
+        rays["o"] = [(0.01 * i, 0, 0) for i in range(64)]
+        rays["d"] = (0, 0, -1)
+        want, _ = oracle.trace_bvh(nodes, so, 12, rays)
+        assert_hits_equal(bvh.trace_closest_hit(rays), want, "coincident spheres")
+        bvh.close()
+    finally:
+        gpu.set_ray_mode(gpu.RAYS_WIDE)
