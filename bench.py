@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--spheres", type=int, default=N_SPHERES)
+    ap.add_argument("--config5", action="store_true",
+                    help="also run BASELINE config 5 on this GPU's share: 10 M spheres, 8K frame, primary + bounce batches "
+                         "(host build ~40 s; not part of the default run)")
     return ap.parse_args()
 
 
@@ -453,6 +456,11 @@ def run_sweep(torch, pkg, bvh1m, spheres1m, args, flush, stream, peaks):
             rec.update(extra)
         out.append(rec)
 
+    # config 1: benchmark.c as the repo runs it (srand(1) instead of time(NULL)): n = 5 000 .. 50 000, centres
+    # U[-500,500)^3, r = 0.5, build(0, n-1, 20) (benchmark.c:317), 10 000 rays for benchmark_no_bvh and the NEXT
+    # 10 000 of the same rand() stream for benchmark_with_bvh; rows in benchmark_data.txt's "%d %f %f" format.
+    out.append(config1_as_shipped(pkg, args))
+
     # config 2: default renderer scene, 800x600
     pkg.srand(1)
     s20 = pkg.random_scene(20)
@@ -499,7 +507,113 @@ def run_sweep(torch, pkg, bvh1m, spheres1m, args, flush, stream, peaks):
     dt = (time.perf_counter() - t0) / 3
     out[-1]["e2e"] = {"value": n_b / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 24 * n_b, "d2h_bytes_per_step": 32 * n_b,
                       "api": "gpu_trace_closest_hit (pinned host buffers)"}
+    if args.config5:
+        out.append(config5_10m(torch, pkg, args, stream))
     return out
+
+
+def config5_10m(torch, pkg, args, stream):
+    """BASELINE config 5 on ONE GPU: 10 M spheres (tree HBM resident: 640 MB binary + 300 MB wide + 160 MB
+    spheres, replicated per GPU), 7680x4320 frame; 16 spp = 1 primary batch + 15 diffuse-bounce batches per
+    pixel (the reference has no pixel jitter).  One bounce batch is timed and counted 15 times."""
+    n = 10_000_000
+    W, H = 7680, 4320
+    pkg.srand(1)
+    s = pkg.benchmark_scene(n)
+    t0 = time.perf_counter()
+    bvh = pkg.GpuBvh.build(s, n, 0, n, 0)
+    build_s = time.perf_counter() - t0
+    cam = pkg.default_camera()
+    buf = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
+    steps = 5
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms_p = timed(lambda: bvh.trace_primary_dev(cam, W, H, 0, H, buf.data_ptr(), stream))
+    st_p = bvh.trace_primary_stats(cam, W, H, 0, H, buf.data_ptr())
+    hits = buf.cpu().numpy().view(pkg.HIT_DT).reshape(-1)
+    pkg.srand(2)
+    rays = pkg.bounce_rays(hits)
+    while len(rays) < W * H:
+        rays = np.concatenate([rays, pkg.bounce_rays(hits)])
+    rays = rays[:W * H]
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 6)).cuda()
+    ms_b = timed(lambda: bvh.trace_closest_hit_dev(d_rays.data_ptr(), W * H, buf.data_ptr(), stream))
+    st_b = bvh.trace_closest_hit_stats(d_rays.data_ptr(), W * H, buf.data_ptr())
+    info = bvh.info()
+    bvh.close()
+    total_ms = ms_p + 15 * ms_b
+    return {"workload": "config 5 on one GPU: 10M random spheres, 7680x4320, 16 spp = 1 primary + 15 bounce batches",
+            "rays": 16 * W * H, "ms_per_step": total_ms, "value": 16 * W * H / (total_ms * 1e-3) / 1e9, "unit": UNIT,
+            "primary": {"ms": ms_p, "value": W * H / (ms_p * 1e-3) / 1e9, "nodes_per_tile_or_ray": st_p["inner_visits"] / max(st_p["rays"], 1),
+                        "hit_rate": st_p["hits"] / max(st_p["rays"], 1)},
+            "bounce": {"ms": ms_b, "value": W * H / (ms_b * 1e-3) / 1e9, "wide_nodes_per_ray": st_b["inner_visits"] / max(st_b["rays"], 1),
+                       "sphere_tests_per_ray": st_b["sphere_tests"] / max(st_b["rays"], 1), "hit_rate": st_b["hits"] / max(st_b["rays"], 1)},
+            "build_and_upload_s_host": build_s, "bvh": info}
+
+
+def config1_as_shipped(pkg, args):
+    """SURVEY 8(d) config 1.  GPU seconds are wall-clock around the host-buffer C-ABI calls
+    (gpu_benchmark_no_bvh / gpu_benchmark_with_bvh: H2D of the rays, kernels, 8 bytes back).  The CPU
+    columns time the reference's own loops (oracle/_ref, else the oracle port) on the SAME ray arrays,
+    1 core as the repo runs; brute force on a ray subset, scaled (10 000 x 50 000 tests take ~20 s)."""
+    rows = []
+    cpu = None
+    if not args.no_cpu:
+        from oracle.oracle_py import Oracle, RefLib, ref_available
+        cpu = RefLib() if ref_available() else Oracle()
+    pkg.srand(1)
+    n_rays = 10000
+    for n in range(5000, 50001, 5000):
+        s = pkg.benchmark_scene(n)
+        s_unbuilt = s.copy()
+        t0 = time.perf_counter()
+        bvh = pkg.GpuBvh.build(s, n, 0, n - 1, 20)
+        build_s = time.perf_counter() - t0
+        rays_a, rays_b = pkg.benchmark_rays(n_rays), pkg.benchmark_rays(n_rays)
+        bvh.benchmark_no_bvh(rays_a[:64]); bvh.benchmark_with_bvh(rays_b[:64])   # staging buffers, module load
+        t0 = time.perf_counter(); hits_a = bvh.benchmark_no_bvh(rays_a); t_a = time.perf_counter() - t0
+        t0 = time.perf_counter(); hits_b = bvh.benchmark_with_bvh(rays_b); t_b = time.perf_counter() - t0
+        row = {"n_spheres": n, "gpu_no_bvh_s": t_a, "gpu_with_bvh_s": t_b, "intersections_no_bvh": hits_a,
+               "intersections_with_bvh": hits_b, "gpu_build_and_upload_s": build_s,
+               "multi_leaves": bvh.info()["multi_leaves"]}
+        bvh.close()
+        if cpu is not None and n in (5000, 25000, 50000):
+            sub = 500
+            if hasattr(cpu, "export_tree"):          # compiled reference
+                root, _ = cpu.build(s_unbuilt, 0, n - 1, 20)
+                hb, sec_b = cpu.trace_bvh(root, s_unbuilt, rays_b, 1)
+                ha, sec_a = cpu.trace_brute(s_unbuilt, n, rays_a[:sub], 1)
+                cpu.free(root)
+                kind = "reference"
+            else:
+                nodes = cpu.build(s_unbuilt, 0, n - 1, 20)
+                hb, sec_b = cpu.trace_bvh(nodes, s_unbuilt, n, rays_b, 1)
+                ha, sec_a = cpu.trace_brute(s_unbuilt, n, rays_a[:sub], 1)
+                kind = "port"
+            row.update({"cpu_with_bvh_s": sec_b, "cpu_no_bvh_s": sec_a * n_rays / sub, "cpu_kind": kind, "cpu_cores": 1,
+                        "cpu_no_bvh_sample": f"{sub} of {n_rays} rays, scaled",
+                        "cpu_intersections_with_bvh": int((hb["prim"] >= 0).sum())})
+        rows.append(row)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "benchmark_data.txt"), "w") as f:
+            for r in rows:
+                f.write("%d %f %f\n" % (r["n_spheres"], r["gpu_no_bvh_s"], r["gpu_with_bvh_s"]))   # benchmark.c:168
+    except OSError:
+        pass
+    return {"workload": "benchmark.c as shipped: n = 5000..50000, build(0,n-1,20), 10000 + 10000 rays, seconds per call "
+                        "(benchmark_data.txt columns: n, no-BVH s, with-BVH s)", "rows": rows}
 
 
 def main():

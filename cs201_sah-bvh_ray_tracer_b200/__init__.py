@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "gpu_trace_closest_hit", "gpu_trace_closest_hit_dev", "gpu_trace_primary", "gpu_trace_primary_dev",
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
     "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
+    "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
@@ -255,6 +256,20 @@ class GpuBvh:
         out = np.empty(len(rays), HIT_DT)
         _check(lib.gpu_trace_brute_force(self._h, _ptr(rays), C.c_int64(len(rays)), _ptr(out)), "gpu_trace_brute_force")
         return out
+
+    def benchmark_no_bvh(self, rays: np.ndarray) -> int:
+        """benchmark.c:172-223: number of rays that hit any sphere (every sphere tested, no BVH)."""
+        rays = np.ascontiguousarray(rays)
+        out = C.c_int64(0)
+        _check(lib.gpu_benchmark_no_bvh(self._h, _ptr(rays), C.c_int64(len(rays)), C.byref(out)), "gpu_benchmark_no_bvh")
+        return int(out.value)
+
+    def benchmark_with_bvh(self, rays: np.ndarray) -> int:
+        """benchmark.c:225-254: number of rays whose closest hit exists."""
+        rays = np.ascontiguousarray(rays)
+        out = C.c_int64(0)
+        _check(lib.gpu_benchmark_with_bvh(self._h, _ptr(rays), C.c_int64(len(rays)), C.byref(out)), "gpu_benchmark_with_bvh")
+        return int(out.value)
 
     # ---- device-pointer entry points (asynchronous on `stream`) ----
     def trace_closest_hit_dev(self, d_rays: int, n: int, d_out: int, stream: int = 0):

@@ -624,6 +624,68 @@ k_brute_force(const float *__restrict__ spheres4, SahScene sc, const float *__re
     }
 }
 
+/*
+ * K4: benchmark.c's two counting loops.
+ *  k_any_hit_flags  benchmark_no_bvh (benchmark.c:172-223): every ray against EVERY sphere, no early
+ *                   exit, "hit" = ray_sphere_intersect(...).hit_something (hit.c:27-29); a ray counts
+ *                   once (any-hit counting, not closest hit).  grid.y splits the spheres so
+ *                   that 10 000 rays still fill the device; per-ray flags are OR-ed in global memory.
+ *  k_count_flags / k_count_prims  the final `intersections++` reductions (flags, or prim >= 0 of a
+ *                   hit buffer for benchmark_with_bvh, benchmark.c:225-254).
+ */
+#define ANYHIT_SPHERES_PER_BLOCK 4096
+
+__global__ void __launch_bounds__(TRACE_THREADS)
+k_any_hit_flags(const float *__restrict__ spheres4, SahScene sc, const float *__restrict__ rays, long long n,
+                unsigned int *__restrict__ flags)
+{
+    __shared__ float4 tile[TRACE_THREADS];
+    const long long i = (long long)blockIdx.x * TRACE_THREADS + threadIdx.x;
+    const bool live = i < n;
+    SahRay r;
+    if (live) {
+        const float *rp = rays + i * 6;
+        sah_ray_setup(r, rp[0], rp[1], rp[2], rp[3], rp[4], rp[5], sc);
+    } else {
+        sah_ray_setup(r, 0, 0, 0, 0, 0, 0, sc);
+    }
+    const int s0 = blockIdx.y * ANYHIT_SPHERES_PER_BLOCK;
+    const int s1 = min(sc.n_spheres, s0 + ANYHIT_SPHERES_PER_BLOCK);
+    bool any = false;
+    for (int base = s0; base < s1; base += TRACE_THREADS) {
+        const int j = base + threadIdx.x;
+        tile[threadIdx.x] = j < s1 ? reinterpret_cast<const float4 *>(spheres4)[j]
+                                   : make_float4(0, 0, 0, __int_as_float(0x7fffffff));
+        __syncthreads();
+        const int m = min(TRACE_THREADS, s1 - base);
+        if (live) {
+            for (int k = 0; k < m; k++) {
+                const float4 s = tile[k];
+                float t;
+                any |= sah_sphere_t(r, s.x, s.y, s.z, s.w, t);
+            }
+        }
+        __syncthreads();
+    }
+    if (live && any) atomicOr(&flags[i], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_count_flags(const unsigned int *__restrict__ flags, long long n, unsigned long long *count)
+{
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) c += flags[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+__global__ void __launch_bounds__(256) k_count_prims(const gpu_hit *__restrict__ hits, long long n, unsigned long long *count)
+{
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) c += hits[i].prim >= 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* handle                                                                                       */
 /* ------------------------------------------------------------------------------------------ */
@@ -1113,6 +1175,76 @@ extern "C" int gpu_trace_brute_force(gpu_bvh *b, const Ray *rays, int64_t n, gpu
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(out, b->d_out[0], (size_t)n * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    return SAHBVH_OK;
+}
+
+/* benchmark.c:172-223 on the device: rays in, number of rays that hit ANY of the handle's spheres out */
+extern "C" int gpu_benchmark_no_bvh(gpu_bvh *b, const Ray *rays, int64_t n, int64_t *intersections)
+{
+    if (!b || n < 0 || !intersections || (n > 0 && !rays)) {
+        sahbvh_set_error("gpu_benchmark_no_bvh: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    *intersections = 0;
+    if (n == 0 || b->info.n_spheres == 0) return SAHBVH_OK;
+    DeviceGuard guard(b->device);
+    int rc = ensure_staging(b, (size_t)n * sizeof(Ray), (size_t)n * sizeof(gpu_hit));
+    if (rc != SAHBVH_OK) return rc;
+    cudaStream_t st = b->streams[0];
+    unsigned int *flags = (unsigned int *)b->d_out[0];
+    unsigned long long *cnt = b->d_counters + 7;
+    CU_TRY(cudaMemcpyAsync(b->d_in[0], rays, (size_t)n * sizeof(Ray), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(flags, 0, (size_t)n * sizeof(unsigned int), st));
+    CU_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+    dim3 grid((unsigned)((n + TRACE_THREADS - 1) / TRACE_THREADS),
+              (unsigned)((b->info.n_spheres + ANYHIT_SPHERES_PER_BLOCK - 1) / ANYHIT_SPHERES_PER_BLOCK));
+    k_any_hit_flags<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, make_scene(b->info), (const float *)b->d_in[0], n, flags);
+    int cblocks = (int)((n + 255) / 256);
+    if (cblocks > b->sm_count * 8) cblocks = b->sm_count * 8;
+    k_count_flags<<<cblocks, 256, 0, st>>>(flags, n, cnt);
+    g_launches += 2;
+    CU_TRY(cudaGetLastError());
+    unsigned long long h = 0;
+    CU_TRY(cudaMemcpyAsync(&h, cnt, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    *intersections = (int64_t)h;
+    return SAHBVH_OK;
+}
+
+/* benchmark.c:225-254 on the device: rays in, number of rays whose closest hit exists out (8 bytes back) */
+extern "C" int gpu_benchmark_with_bvh(gpu_bvh *b, const Ray *rays, int64_t n, int64_t *intersections)
+{
+    if (!b || n < 0 || !intersections || (n > 0 && !rays)) {
+        sahbvh_set_error("gpu_benchmark_with_bvh: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    *intersections = 0;
+    if (n == 0) return SAHBVH_OK;
+    DeviceGuard guard(b->device);
+    long long chunk = n < HOST_CHUNK_RAYS ? n : HOST_CHUNK_RAYS;
+    int rc = ensure_staging(b, (size_t)chunk * sizeof(Ray), (size_t)chunk * sizeof(gpu_hit));
+    if (rc != SAHBVH_OK) return rc;
+    unsigned long long *cnt = b->d_counters + 7;
+    CU_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), b->streams[0]));
+    CU_TRY(cudaStreamSynchronize(b->streams[0]));
+    int k = 0;
+    for (long long off = 0; off < n; off += chunk, k ^= 1) {
+        long long m = n - off < chunk ? n - off : chunk;
+        cudaStream_t st = b->streams[k];
+        CU_TRY(cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
+        rc = launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
+        if (rc != SAHBVH_OK) return rc;
+        int cblocks = (int)((m + 255) / 256);
+        if (cblocks > b->sm_count * 8) cblocks = b->sm_count * 8;
+        k_count_prims<<<cblocks, 256, 0, st>>>((const gpu_hit *)b->d_out[k], m, cnt);
+        g_launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaStreamSynchronize(b->streams[0]));
+    CU_TRY(cudaStreamSynchronize(b->streams[1]));
+    unsigned long long h = 0;
+    CU_TRY(cudaMemcpy(&h, cnt, sizeof h, cudaMemcpyDeviceToHost));
+    *intersections = (int64_t)h;
     return SAHBVH_OK;
 }
 

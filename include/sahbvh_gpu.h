@@ -121,6 +121,14 @@ int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, 
  * Parity aid for small n. */
 int gpu_trace_brute_force(gpu_bvh *bvh, const Ray *rays, int64_t n, gpu_hit *out);
 
+/* benchmark.c's two counting loops on the device, rays supplied by the caller:
+ *   gpu_benchmark_no_bvh   = benchmark_no_bvh  (benchmark.c:172-223): every ray against EVERY sphere of the
+ *                            handle, no early exit; *intersections = rays with at least one hit_something
+ *   gpu_benchmark_with_bvh = benchmark_with_bvh (benchmark.c:225-254): *intersections = rays whose
+ *                            ray_bvh_intersect record has hit_something (only 8 bytes come back) */
+int gpu_benchmark_no_bvh(gpu_bvh *bvh, const Ray *rays, int64_t n, int64_t *intersections);
+int gpu_benchmark_with_bvh(gpu_bvh *bvh, const Ray *rays, int64_t n, int64_t *intersections);
+
 /* Instrumented trace (counts work per ray; slower; same hits). */
 int gpu_trace_closest_hit_stats(gpu_bvh *bvh, const void *d_rays, int64_t n, void *d_out, gpu_trace_stats *stats);
 int gpu_trace_primary_stats(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,

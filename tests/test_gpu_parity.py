@@ -208,6 +208,23 @@ def test_1m_primary_and_bounce_vs_oracle(gpu, oracle, scene1m):
     assert same(bh[:2048]["t"], b["t"])
 
 
+def test_benchmark_counting_loops(gpu, oracle, golden):
+    """gpu_benchmark_no_bvh / gpu_benchmark_with_bvh = benchmark.c:172-254's two `intersections` counters."""
+    answers, _ = golden
+    for n in (5000, 50000):
+        case = answers["cases"][f"bench_{n}_asshipped"]
+        gpu.srand(1)
+        s = gpu.benchmark_scene(n)
+        bvh = gpu.GpuBvh.build(s, n, 0, n - 1, 20)
+        rays = gpu.benchmark_rays(10000)
+        assert sha(rays) == case["sha_rays"]
+        assert bvh.benchmark_with_bvh(rays) == case["hits"]
+        want, _ = oracle.trace_brute(s, n, rays)          # any hit <=> a closest hit exists
+        assert bvh.benchmark_no_bvh(rays) == int((want["prim"] >= 0).sum())
+        assert bvh.benchmark_no_bvh(rays[:0]) == 0 and bvh.benchmark_with_bvh(rays[:1]) in (0, 1)
+        bvh.close()
+
+
 # ---------------------------------------------------------------- edge cases
 def test_tiny_trees_and_zero_directions(gpu, oracle):
     for n in (0, 1, 2, 3):
