@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "gpu_trace_closest_hit", "gpu_trace_closest_hit_dev", "gpu_trace_primary", "gpu_trace_primary_dev",
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
     "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
-    "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh",
+    "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
@@ -125,6 +125,35 @@ RAYS_ONE_SHOT, RAYS_COOP, RAYS_WIDE = 0, 1, 2
 
 def set_ray_mode(mode: int):
     _check(lib.sahbvh_set_ray_mode(C.c_int(mode)), "sahbvh_set_ray_mode")
+
+
+BUILD_HOST, BUILD_DEVICE = 0, 1
+
+
+def set_build_mode(mode: int):
+    _check(lib.sahbvh_set_build_mode(C.c_int(mode)), "sahbvh_set_build_mode")
+
+
+TREE_NODE_DT = np.dtype([("lo", np.float32, 3), ("hi", np.float32, 3), ("left", np.int32), ("right", np.int32),
+                         ("sphere", np.int32), ("count", np.int32)])    # sahbvh_tree_node
+
+
+def build_tree(spheres: np.ndarray, start: int, end: int, depth: int = 0, mode: int = BUILD_DEVICE, device: int = -1) -> np.ndarray:
+    """sahbvh_build_tree: preorder array tree; permutes ``spheres`` in place like build_bvh_node."""
+    lib.sahbvh_build_tree.restype = C.c_int64
+    cap = 2 * max(end - start, 1) + 1024      # exact for trees without empty leaves; retried below otherwise
+    backup = spheres.copy()
+    for _ in range(2):
+        out = np.empty(cap, TREE_NODE_DT)
+        n = lib.sahbvh_build_tree(_ptr(spheres), C.c_int(start), C.c_int(end), C.c_int(depth), C.c_int(mode), C.c_int(device),
+                                  _ptr(out), C.c_int64(cap))
+        if n < 0:
+            raise SahBvhError(f"sahbvh_build_tree failed ({n}): {lib.sahbvh_last_error().decode()}")
+        if n <= cap:
+            return out[:n].copy()
+        cap = int(n)
+        spheres[:] = backup                    # the build permuted the array; start again from the input order
+    raise SahBvhError("sahbvh_build_tree: node count changed between two runs")
 
 
 def set_primary_mode(mode: int):

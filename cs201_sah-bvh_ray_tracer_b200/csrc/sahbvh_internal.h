@@ -69,6 +69,10 @@ int sah_tree_from_pointers(sah_tree *t, const BVHNode *root, const Sphere *base,
 int flat_bvh_from_tree(flat_bvh *f, const sah_tree *t, const Sphere *spheres, int n);
 void flat_bvh_release(flat_bvh *f);
 
+/* gpu_builder.cu: same tree and permutation as sah_build, built on the device (falls back to sah_build for
+ * tiny ranges and when a degenerate input outgrows its node pool) */
+int sah_build_gpu(sah_tree *t, Sphere *spheres, int start, int end, int depth, int device);
+
 /* wide.c */
 int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f);
 void wide_bvh_release(wide_bvh *w);

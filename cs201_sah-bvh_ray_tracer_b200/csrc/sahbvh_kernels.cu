@@ -33,6 +33,14 @@ static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_PACKET};
 static std::atomic<int> g_ray_mode{SAHBVH_RAYS_WIDE};
+static std::atomic<int> g_build_mode{SAHBVH_BUILD_DEVICE};
+
+extern "C" int sahbvh_set_build_mode(int mode)
+{
+    if (mode != SAHBVH_BUILD_HOST && mode != SAHBVH_BUILD_DEVICE) return SAHBVH_E_ARG;
+    g_build_mode.store(mode);
+    return SAHBVH_OK;
+}
 
 extern "C" int sahbvh_set_ray_mode(int mode)
 {
@@ -839,7 +847,16 @@ extern "C" int gpu_bvh_build(Sphere *spheres, int n_total, int start, int end, i
     sah_tree t;
     int rc = sah_tree_init(&t, 2 * (int64_t)(end - start + 1) + 16);
     if (rc != SAHBVH_OK) return rc;
-    rc = sah_build(&t, spheres, start, end, depth);
+    if (g_build_mode.load() == SAHBVH_BUILD_DEVICE && end - start >= 4096) {
+        if (sahbvh_device_count() == 0) {
+            sahbvh_set_error("no usable CUDA device; this library has no CPU traversal path");
+            sah_tree_free(&t);
+            return SAHBVH_E_CUDA;
+        }
+        rc = sah_build_gpu(&t, spheres, start, end, depth, device);
+    } else {
+        rc = sah_build(&t, spheres, start, end, depth);
+    }
     flat_bvh f;
     memset(&f, 0, sizeof f);
     if (rc == SAHBVH_OK) rc = flat_bvh_from_tree(&f, &t, spheres, n_total);
@@ -847,6 +864,29 @@ extern "C" int gpu_bvh_build(Sphere *spheres, int n_total, int start, int end, i
     flat_bvh_release(&f);
     sah_tree_free(&t);
     return rc;
+}
+
+static_assert(sizeof(sahbvh_tree_node) == sizeof(sah_node), "public tree node == internal tree node");
+
+extern "C" int64_t sahbvh_build_tree(Sphere *spheres, int start, int end, int depth, int mode, int device,
+                                     sahbvh_tree_node *out, int64_t cap)
+{
+    if (!spheres || !out || start < 0 || end < start || cap < 0 || (mode != SAHBVH_BUILD_HOST && mode != SAHBVH_BUILD_DEVICE)) {
+        sahbvh_set_error("sahbvh_build_tree: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    if (mode == SAHBVH_BUILD_DEVICE && sahbvh_device_count() == 0) {
+        sahbvh_set_error("no usable CUDA device");
+        return SAHBVH_E_CUDA;
+    }
+    sah_tree t;
+    int rc = sah_tree_init(&t, 2 * (int64_t)(end - start + 1) + 16);
+    if (rc != SAHBVH_OK) return rc;
+    rc = mode == SAHBVH_BUILD_DEVICE ? sah_build_gpu(&t, spheres, start, end, depth, device) : sah_build(&t, spheres, start, end, depth);
+    int64_t used = rc == SAHBVH_OK ? t.used : (int64_t)rc;
+    if (rc == SAHBVH_OK && used <= cap) memcpy(out, t.nodes, (size_t)used * sizeof(sah_node));
+    sah_tree_free(&t);
+    return used;
 }
 
 extern "C" void gpu_bvh_free(gpu_bvh *b)

@@ -73,10 +73,29 @@ const char *sahbvh_version(void);
  * The handle owns copies; host arrays may be freed after the call. */
 int gpu_bvh_upload(const Sphere *permuted, int n, const BVHNode *root, int device, gpu_bvh **out);
 
-/* Build (host, binned SAH, identical topology and permutation to bvh.c:117-209) directly into
+/* Build (binned SAH, identical topology, bounds and permutation to bvh.c:117-209) directly into
  * the flattened form, skipping the per-node mallocs, then upload.  Permutes spheres[start,end)
- * in place exactly like build_bvh_node; n_total is the array length (indices are global). */
+ * in place exactly like build_bvh_node; n_total is the array length (indices are global).
+ * Ranges of >= 4096 spheres are built ON THE DEVICE (level-parallel binning, exact replay of the
+ * reference's swap order), smaller ones by the host builder; sahbvh_set_build_mode selects. */
 int gpu_bvh_build(Sphere *spheres, int n_total, int start, int end, int depth, int device, gpu_bvh **out);
+#define SAHBVH_BUILD_HOST 0
+#define SAHBVH_BUILD_DEVICE 1
+int sahbvh_set_build_mode(int mode);
+
+/* The built tree as a preorder array (root = 0), one entry per reference BVHNode, for callers that want
+ * the tree itself rather than a device handle (and for checking the device builder against bvh.c):
+ * runs the selected builder (mode = SAHBVH_BUILD_HOST / SAHBVH_BUILD_DEVICE) over spheres[start,end),
+ * permutes the array exactly like build_bvh_node and writes up to `cap` nodes.  Returns the node
+ * count (> cap means the array was too small and nothing was written) or a negative error code. */
+typedef struct sahbvh_tree_node {
+    float lo[3], hi[3];   /* node->bounds (bvh.c:120-125) */
+    int32_t left, right;  /* preorder ids of the children; -1 on leaves */
+    int32_t sphere;       /* leaf: index of spheres[start], the only sphere hit.c:98-99 tests; -1 on inner nodes */
+    int32_t count;        /* leaf: sphere_count */
+} sahbvh_tree_node;
+int64_t sahbvh_build_tree(Sphere *spheres, int start, int end, int depth, int mode, int device,
+                          sahbvh_tree_node *out, int64_t cap);
 
 void gpu_bvh_free(gpu_bvh *bvh);
 int gpu_bvh_get_info(const gpu_bvh *bvh, gpu_bvh_info *info);

@@ -482,3 +482,69 @@ def test_ray_buffer_kernels_on_degenerate_trees(gpu, oracle, golden, mode):
         bvh.close()
     finally:
         gpu.set_ray_mode(gpu.RAYS_WIDE)
+
+
+# ---------------------------------------------------------------- device SAH builder
+@pytest.mark.parametrize("kind,n,build", [
+    ("bench", 5000, (0, 4999, 20)), ("bench", 50000, (0, 49999, 20)), ("bench", 200000, (0, 199999, 20)),
+    ("bench", 100000, (0, 100000, 0)), ("bench", 1000000, (0, 1000000, 0)), ("random", 5000, (0, 5000, 0)),
+    ("random", 60000, (0, 60000, 0)), ("random", 20000, (1000, 19000, 3)), ("bench", 4097, (0, 4097, 38)),
+])
+def test_device_builder_matches_reference_tree(gpu, oracle, kind, n, build):
+    """sahbvh_build_tree(SAHBVH_BUILD_DEVICE) == the oracle's tree (bounds, topology, leaf sphere, count) and the
+    same in-place sphere permutation, byte for byte -- including depth-capped multi-sphere leaves (Q2)."""
+    from common import NODE_DT
+    oracle.srand(90 + n % 97)
+    so = oracle.scene_benchmark(n) if kind == "bench" else oracle.scene_random(n)
+    sd, sh = so.copy(), so.copy()
+    nodes = oracle.build(so, *build)
+    tree_d = gpu.build_tree(sd, *build, mode=gpu.BUILD_DEVICE)
+    assert same(sd, so), "device builder: sphere permutation"
+    assert len(tree_d) == len(nodes)
+    assert same(tree_d.view(np.uint8), nodes.view(NODE_DT).view(np.uint8)), "device builder: tree"
+    tree_h = gpu.build_tree(sh, *build, mode=gpu.BUILD_HOST)
+    assert same(sh, so) and same(tree_h, tree_d)
+
+
+def test_device_builder_degenerate_inputs(gpu, oracle):
+    """Coincident spheres (all 21 costs NaN -> x < 0.0f fallback chains), huge radii, NaN/inf
+    coordinates: the device builder hands such nodes to its serial pass and must still equal the host builder."""
+    rng = np.random.default_rng(3)
+    n = 20000
+    base = np.zeros(n + 1, SPHERE_DT)
+    base["c"][:n] = rng.uniform(-100, 100, size=(n, 3)).astype(np.float32)
+    base["r"][:n] = 0.5
+    cases = []
+    a = base.copy(); a["c"][:6000] = (3.0, -2.0, 1.0); cases.append(("6000 coincident", a))
+    b = base.copy(); b["c"][100:400, 0] = 7.0; b["r"][5] = 1e30; cases.append(("huge radius", b))
+    c = base.copy(); c["c"][17] = (np.nan, 0, 0); c["c"][18] = (np.inf, 1, 2); c["r"][19] = np.nan; cases.append(("nan/inf", c))
+    d = base.copy(); d["c"][:n] = np.round(d["c"][:n] / 50) * 50; cases.append(("lattice duplicates", d))
+    for name, s in cases:
+        sd, sh = s.copy(), s.copy()
+        th = gpu.build_tree(sh, 0, n, 0, mode=gpu.BUILD_HOST)
+        td = gpu.build_tree(sd, 0, n, 0, mode=gpu.BUILD_DEVICE)
+        assert same(sd, sh), name + ": permutation"
+        assert len(td) == len(th) and same(td, th), name + ": tree"
+
+
+def test_gpu_bvh_build_uses_device_builder_and_traces_identically(gpu, oracle):
+    oracle.srand(4)
+    so = oracle.scene_benchmark(300000)
+    nodes = oracle.build(so.copy(), 0, 300000, 0)
+    rays = oracle.rays_benchmark(20000)
+    want = None
+    try:
+        for mode in (gpu.BUILD_HOST, gpu.BUILD_DEVICE):
+            gpu.set_build_mode(mode)
+            s = so.copy()
+            bvh = gpu.GpuBvh.build(s, 300000, 0, 300000, 0)
+            got = bvh.trace_closest_hit(rays)
+            bvh.close()
+            if want is None:
+                ref = so.copy()
+                nodes = oracle.build(ref, 0, 300000, 0)
+                want, _ = oracle.trace_bvh(nodes, ref, 300000, rays)
+            assert same(s, ref)
+            assert_hits_equal(got, want, f"build mode {mode}")
+    finally:
+        gpu.set_build_mode(gpu.BUILD_DEVICE)
