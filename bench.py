@@ -507,6 +507,14 @@ def run_sweep(torch, pkg, bvh1m, spheres1m, args, flush, stream, peaks):
     dt = (time.perf_counter() - t0) / 3
     out[-1]["e2e"] = {"value": n_b / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 24 * n_b, "d2h_bytes_per_step": 32 * n_b,
                       "api": "gpu_trace_closest_hit (pinned host buffers)"}
+    # the whole path loop (trace_ray, MAX_DEPTH 5, 1 sample per pixel) on the 1 M-sphere 4K frame,
+    # counter-based random draws, RGBA8 frame left in HBM; the ray count comes from the per-depth survivors
+    d_rgba = torch.empty((WIDTH * HEIGHT,), dtype=torch.int32, device="cuda")
+    fn = lambda: bvh1m.render_frame_dev(cam, WIDTH, HEIGHT, 0, HEIGHT, 5, 1, d_rgba.data_ptr(), stream)
+    total_ms, _ = time_steps(torch, fn, steps, warm, flush, False)
+    ms = total_ms / steps
+    out.append({"workload": "path loop (renderer.c:21-76): 1M random spheres, 3840x2160, MAX_DEPTH 5, 1 spp, RGBA8 out",
+                "pixels": WIDTH * HEIGHT, "ms_per_step": ms, "value": WIDTH * HEIGHT / (ms * 1e-3) / 1e9, "unit": "Gpaths/s"})
     if args.config5:
         out.append(config5_10m(torch, pkg, args, stream))
     return out

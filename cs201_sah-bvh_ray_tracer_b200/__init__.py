@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
     "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
     "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree",
+    "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
@@ -300,6 +301,26 @@ class GpuBvh:
         _check(lib.gpu_benchmark_with_bvh(self._h, _ptr(rays), C.c_int64(len(rays)), C.byref(out)), "gpu_benchmark_with_bvh")
         return int(out.value)
 
+    def render_frame(self, cam: np.ndarray, width: int, height: int, y0: int = 0, y1: int | None = None, max_depth: int = 5,
+                     seed: int = 0, samples: np.ndarray | None = None) -> np.ndarray:
+        """gpu_render_frame: RGBA8 rows [y0,y1); ``samples`` = float32 [pixels, max_depth, 3] (parity mode) or None."""
+        y1 = height if y1 is None else y1
+        out = np.empty(((y1 - y0) * width, 4), np.uint8)
+        sp = None
+        if samples is not None:
+            sp = np.ascontiguousarray(samples, np.float32)
+            assert sp.shape == ((y1 - y0) * width, max_depth, 3)
+        _check(lib.gpu_render_frame(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                    C.c_int(max_depth), C.c_uint64(seed), _ptr(sp) if sp is not None else None, _ptr(out)),
+               "gpu_render_frame")
+        return out
+
+    def render_frame_dev(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, max_depth: int, seed: int,
+                         d_rgba: int, stream: int = 0):
+        _check(lib.gpu_render_frame_dev(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                        C.c_int(max_depth), C.c_uint64(seed), None, C.c_void_p(d_rgba), C.c_void_p(stream)),
+               "gpu_render_frame_dev")
+
     # ---- device-pointer entry points (asynchronous on `stream`) ----
     def trace_closest_hit_dev(self, d_rays: int, n: int, d_out: int, stream: int = 0):
         _check(lib.gpu_trace_closest_hit_dev(self._h, C.c_void_p(d_rays), C.c_int64(n), C.c_void_p(d_out),
@@ -327,6 +348,20 @@ class GpuBvh:
         _check(lib.gpu_trace_primary_stats(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
                                            C.c_void_p(d_out), C.byref(st)), "gpu_trace_primary_stats")
         return st.as_dict()
+
+
+def accumulate(accum: np.ndarray, frames: int, rgba: np.ndarray) -> np.ndarray:
+    """gpu_accumulate (main.c:368-405): updates ``accum`` (float32 [pixels,3]) in place, returns the shown RGBA8 frame."""
+    assert accum.dtype == np.float32 and accum.flags.c_contiguous
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    avg = np.empty_like(rgba)
+    _check(lib.gpu_accumulate(_ptr(accum), C.c_int(frames), _ptr(rgba), C.c_int64(len(rgba)), _ptr(avg)), "gpu_accumulate")
+    return avg
+
+
+def write_ppm(path: str, rgba: np.ndarray, width: int, height: int):
+    _check(lib.sahbvh_write_ppm(path.encode(), _ptr(np.ascontiguousarray(rgba, np.uint8)), C.c_int(width), C.c_int(height)),
+           "sahbvh_write_ppm")
 
 
 def generate_primary_rays(cam: np.ndarray, width: int, height: int, y0: int = 0, y1: int | None = None,

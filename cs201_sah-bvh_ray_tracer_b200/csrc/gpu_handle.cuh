@@ -1,0 +1,69 @@
+/* gpu_handle.cuh -- the device handle and the launch helpers shared by the CUDA translation units. */
+#ifndef SAHBVH_GPU_HANDLE_CUH
+#define SAHBVH_GPU_HANDLE_CUH
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "sahbvh_internal.h"
+#include "traverse_core.cuh"
+
+struct gpu_bvh {
+    int device;
+    float *d_nodes;
+    float *d_spheres4;
+    uint32_t *d_colors;
+    uint32_t *d_wide;   /* 4-wide quantised nodes (wide.c), 64 B each */
+    float *d_special;   /* special-leaf records, 32 B each */
+    int n_wide, n_special;
+    int wide_blocks_per_sm;
+    unsigned long long *d_counters; /* [0..7] work counters, [8..71] per-launch ray cursors of the persistent kernel */
+    unsigned next_counter;
+    int coop_blocks_per_sm;
+    gpu_bvh_info info;
+    cudaStream_t streams[2];
+    /* staging for the host-buffer entry points (grown on demand) */
+    void *d_in[2];
+    void *d_out[2];
+    size_t in_cap, out_cap;
+    int sm_count;
+    /* path-loop work buffers (render.cu), one allocation grown on demand */
+    void *d_render;
+    size_t render_cap;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (dev != prev && cudaSetDevice(dev) != cudaSuccess) return;
+        ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+
+extern std::atomic<unsigned long long> g_launches;
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            sahbvh_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SAHBVH_E_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+SahScene sahbvh_make_scene(const gpu_bvh_info &info);
+void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c);
+int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count);
+int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
+                          cudaStream_t st, bool count, void *d_ids);
+
+#endif

@@ -305,3 +305,21 @@ HitRecord ray_bvh_intersect(Ray ray, BVHNode *node)
     }
     return rec;
 }
+
+/* ------------------------------------------------------------------ frame output (in place of SDL_RenderDrawPoint) */
+int sahbvh_write_ppm(const char *path, const uint8_t *rgba, int width, int height)
+{
+    if (!path || !rgba || width <= 0 || height <= 0) {
+        sahbvh_set_error("sahbvh_write_ppm: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) {
+        sahbvh_set_error("sahbvh_write_ppm: cannot open %s", path);
+        return SAHBVH_E_ARG;
+    }
+    fprintf(f, "P6\n%d %d\n255\n", width, height);
+    for (size_t i = 0; i < (size_t)width * (size_t)height; i++) fwrite(rgba + 4 * i, 1, 3, f);
+    fclose(f);
+    return SAHBVH_OK;
+}

@@ -23,6 +23,7 @@
 
 #include "sahbvh_internal.h"
 #include "traverse_core.cuh"
+#include "gpu_handle.cuh"
 
 static_assert(sizeof(SahHit) == sizeof(gpu_hit), "hit record");
 static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
@@ -30,7 +31,7 @@ static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 #define TRACE_THREADS 128
 #define PRIMARY_THREADS 256 /* 32 x 8 pixels per CTA, one 8x4 tile per warp */
 
-static std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_PACKET};
 static std::atomic<int> g_ray_mode{SAHBVH_RAYS_WIDE};
 static std::atomic<int> g_build_mode{SAHBVH_BUILD_DEVICE};
@@ -55,15 +56,6 @@ extern "C" int sahbvh_set_primary_mode(int mode)
     g_primary_mode.store(mode);
     return SAHBVH_OK;
 }
-
-#define CU_TRY(expr)                                                                              \
-    do {                                                                                          \
-        cudaError_t _e = (expr);                                                                  \
-        if (_e != cudaSuccess) {                                                                  \
-            sahbvh_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-            return SAHBVH_E_CUDA;                                                                 \
-        }                                                                                         \
-    } while (0)
 
 /* ------------------------------------------------------------------------------------------ */
 /* kernels                                                                                      */
@@ -698,42 +690,6 @@ __global__ void __launch_bounds__(256) k_count_prims(const gpu_hit *__restrict__
 /* handle                                                                                       */
 /* ------------------------------------------------------------------------------------------ */
 
-struct gpu_bvh {
-    int device;
-    float *d_nodes;
-    float *d_spheres4;
-    uint32_t *d_colors;
-    uint32_t *d_wide;   /* 4-wide quantised nodes (wide.c), 64 B each */
-    float *d_special;   /* special-leaf records, 32 B each */
-    int n_wide, n_special;
-    int wide_blocks_per_sm;
-    unsigned long long *d_counters; /* [0..7] work counters, [8..71] per-launch ray cursors of the persistent kernel */
-    unsigned next_counter;
-    int coop_blocks_per_sm;
-    gpu_bvh_info info;
-    cudaStream_t streams[2];
-    /* staging for the host-buffer entry points (grown on demand) */
-    void *d_in[2];
-    void *d_out[2];
-    size_t in_cap, out_cap;
-    int sm_count;
-};
-
-struct DeviceGuard {
-    int prev;
-    bool ok;
-    explicit DeviceGuard(int dev) : prev(-1), ok(false)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess) return;
-        if (dev != prev && cudaSetDevice(dev) != cudaSuccess) return;
-        ok = true;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 extern "C" int sahbvh_device_count(void)
 {
     int n = 0;
@@ -904,6 +860,7 @@ extern "C" void gpu_bvh_free(gpu_bvh *b)
     if (b->d_counters) cudaFree(b->d_counters);
     if (b->d_wide) cudaFree(b->d_wide);
     if (b->d_special) cudaFree(b->d_special);
+    if (b->d_render) cudaFree(b->d_render);
     free(b);
 }
 
@@ -921,7 +878,7 @@ extern "C" int gpu_bvh_get_info(const gpu_bvh *b, gpu_bvh_info *info)
 /* launches                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 
-static SahScene make_scene(const gpu_bvh_info &info)
+SahScene sahbvh_make_scene(const gpu_bvh_info &info)
 {
     SahScene sc;
     sc.n_spheres = info.n_spheres;
@@ -943,10 +900,10 @@ static int trace_grid(const gpu_bvh *b, long long n)
     return (int)blocks;
 }
 
-static int launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count)
+int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count)
 {
     if (n == 0) return SAHBVH_OK;
-    const SahScene sc = make_scene(b->info);
+    const SahScene sc = sahbvh_make_scene(b->info);
     if (g_ray_mode.load() == SAHBVH_RAYS_WIDE) {
         /* persistent grid over the 4-wide tree: every resident warp pulls 128-ray chunks */
         if (b->wide_blocks_per_sm == 0) {
@@ -999,7 +956,7 @@ static int launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out,
     return SAHBVH_OK;
 }
 
-static void make_camera(const Camera *cam, int width, int height, SahCamera *c)
+void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c)
 {
     /* ray.c:18-24, evaluated once per frame on the host with the reference's double/float mix */
     Camera tmp = *cam;
@@ -1018,15 +975,15 @@ static void make_camera(const Camera *cam, int width, int height, SahCamera *c)
     c->fh = (float)height;
 }
 
-static int launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
-                          cudaStream_t st, bool count, void *d_ids = nullptr)
+int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
+                          cudaStream_t st, bool count, void *d_ids)
 {
     if (y1 <= y0 || width <= 0) return SAHBVH_OK;
     SahCamera c;
-    make_camera(cam, width, height, &c);
+    sahbvh_make_camera(cam, width, height, &c);
     gpu_hit *out = (gpu_hit *)d_out;
     float2 *ids = (float2 *)d_ids;
-    const SahScene sc = make_scene(b->info);
+    const SahScene sc = sahbvh_make_scene(b->info);
     if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
         long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + 7) / 8);
         unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
@@ -1091,7 +1048,7 @@ extern "C" int gpu_trace_closest_hit_dev(gpu_bvh *b, const void *d_rays, int64_t
         return SAHBVH_E_ARG;
     }
     DeviceGuard guard(b->device);
-    return launch_rays(b, d_rays, n, d_out, (cudaStream_t)stream, false);
+    return sahbvh_launch_rays(b, d_rays, n, d_out, (cudaStream_t)stream, false);
 }
 
 extern "C" int gpu_trace_closest_hit(gpu_bvh *b, const Ray *rays, int64_t n, gpu_hit *out)
@@ -1110,7 +1067,7 @@ extern "C" int gpu_trace_closest_hit(gpu_bvh *b, const Ray *rays, int64_t n, gpu
         long long m = n - off < chunk ? n - off : chunk;
         cudaStream_t st = b->streams[k];
         CU_TRY(cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
-        rc = launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
+        rc = sahbvh_launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
         if (rc != SAHBVH_OK) return rc;
         CU_TRY(cudaMemcpyAsync(out + off, b->d_out[k], (size_t)m * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
         /* the staging pair k is reused two chunks later: the stream orders it */
@@ -1126,7 +1083,7 @@ extern "C" int gpu_trace_primary_dev(gpu_bvh *b, const Camera *cam, int width, i
     int rc = check_frame(b, cam, width, height, y0, y1, d_out);
     if (rc != SAHBVH_OK) return rc;
     DeviceGuard guard(b->device);
-    return launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false);
+    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, nullptr);
 }
 
 extern "C" int gpu_trace_primary_dev_ids(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
@@ -1135,7 +1092,7 @@ extern "C" int gpu_trace_primary_dev_ids(gpu_bvh *b, const Camera *cam, int widt
     int rc = check_frame(b, cam, width, height, y0, y1, d_out);
     if (rc != SAHBVH_OK) return rc;
     DeviceGuard guard(b->device);
-    return launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_ids);
+    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_ids);
 }
 
 extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out)
@@ -1154,7 +1111,7 @@ extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int h
     for (int ya = y0; ya < y1; ya += band, k ^= 1) {
         int yb = ya + band < y1 ? ya + band : y1;
         cudaStream_t st = b->streams[k];
-        rc = launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false);
+        rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false, nullptr);
         if (rc != SAHBVH_OK) return rc;
         CU_TRY(cudaMemcpyAsync(out + (size_t)(ya - y0) * (size_t)width, b->d_out[k],
                                (size_t)(yb - ya) * (size_t)width * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
@@ -1179,7 +1136,7 @@ extern "C" int gpu_generate_primary_rays(const Camera *cam, int width, int heigh
     if (device < 0) CU_TRY(cudaGetDevice(&device));
     DeviceGuard guard(device);
     SahCamera c;
-    make_camera(cam, width, height, &c);
+    sahbvh_make_camera(cam, width, height, &c);
     size_t bytes = (size_t)(y1 - y0) * (size_t)width * sizeof(Ray);
     float *d = nullptr;
     CU_TRY(cudaMalloc(&d, bytes));
@@ -1209,7 +1166,7 @@ extern "C" int gpu_trace_brute_force(gpu_bvh *b, const Ray *rays, int64_t n, gpu
     cudaStream_t st = b->streams[0];
     CU_TRY(cudaMemcpyAsync(b->d_in[0], rays, (size_t)n * sizeof(Ray), cudaMemcpyHostToDevice, st));
     int grid = (int)((n + TRACE_THREADS - 1) / TRACE_THREADS);
-    k_brute_force<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, make_scene(b->info), (const float *)b->d_in[0], n,
+    k_brute_force<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, sahbvh_make_scene(b->info), (const float *)b->d_in[0], n,
                                                  (gpu_hit *)b->d_out[0]);
     g_launches++;
     CU_TRY(cudaGetLastError());
@@ -1238,7 +1195,7 @@ extern "C" int gpu_benchmark_no_bvh(gpu_bvh *b, const Ray *rays, int64_t n, int6
     CU_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
     dim3 grid((unsigned)((n + TRACE_THREADS - 1) / TRACE_THREADS),
               (unsigned)((b->info.n_spheres + ANYHIT_SPHERES_PER_BLOCK - 1) / ANYHIT_SPHERES_PER_BLOCK));
-    k_any_hit_flags<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, make_scene(b->info), (const float *)b->d_in[0], n, flags);
+    k_any_hit_flags<<<grid, TRACE_THREADS, 0, st>>>(b->d_spheres4, sahbvh_make_scene(b->info), (const float *)b->d_in[0], n, flags);
     int cblocks = (int)((n + 255) / 256);
     if (cblocks > b->sm_count * 8) cblocks = b->sm_count * 8;
     k_count_flags<<<cblocks, 256, 0, st>>>(flags, n, cnt);
@@ -1272,7 +1229,7 @@ extern "C" int gpu_benchmark_with_bvh(gpu_bvh *b, const Ray *rays, int64_t n, in
         long long m = n - off < chunk ? n - off : chunk;
         cudaStream_t st = b->streams[k];
         CU_TRY(cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
-        rc = launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
+        rc = sahbvh_launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
         if (rc != SAHBVH_OK) return rc;
         int cblocks = (int)((m + 255) / 256);
         if (cblocks > b->sm_count * 8) cblocks = b->sm_count * 8;
@@ -1309,7 +1266,7 @@ extern "C" int gpu_trace_closest_hit_stats(gpu_bvh *b, const void *d_rays, int64
     }
     DeviceGuard guard(b->device);
     CU_TRY(cudaMemset(b->d_counters, 0, 8 * sizeof(unsigned long long)));
-    int rc = launch_rays(b, d_rays, n, d_out, 0, true);
+    int rc = sahbvh_launch_rays(b, d_rays, n, d_out, 0, true);
     if (rc != SAHBVH_OK) return rc;
     CU_TRY(cudaDeviceSynchronize());
     return read_counters(b, (uint64_t)n, stats);
@@ -1323,7 +1280,7 @@ extern "C" int gpu_trace_primary_stats(gpu_bvh *b, const Camera *cam, int width,
     if (!stats) return SAHBVH_E_ARG;
     DeviceGuard guard(b->device);
     CU_TRY(cudaMemset(b->d_counters, 0, 8 * sizeof(unsigned long long)));
-    rc = launch_primary(b, cam, width, height, y0, y1, d_out, 0, true);
+    rc = sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, 0, true, nullptr);
     if (rc != SAHBVH_OK) return rc;
     CU_TRY(cudaDeviceSynchronize());
     return read_counters(b, (uint64_t)(y1 - y0) * (uint64_t)width, stats);

@@ -148,6 +148,27 @@ int gpu_trace_brute_force(gpu_bvh *bvh, const Ray *rays, int64_t n, gpu_hit *out
 int gpu_benchmark_no_bvh(gpu_bvh *bvh, const Ray *rays, int64_t n, int64_t *intersections);
 int gpu_benchmark_with_bvh(gpu_bvh *bvh, const Ray *rays, int64_t n, int64_t *intersections);
 
+/* The path loop around the closest hit: main.c:356-366 + trace_ray renderer.c:21-76 for
+ * image rows [y0,y1), one sample per pixel, as a wavefront: fused primary rays, then one ray-buffer launch per
+ * bounce depth over the rays still alive, colour blend (Uint8)(base + 0.5 * reflected) folded back in the
+ * recursion's order, sky gradient on a miss, black when max_depth (MAX_DEPTH = 5, constants.h:5) is exhausted.
+ * Output: SDL_Color-layout RGBA8, 4 bytes per pixel.
+ *   samples != NULL : [pixel][max_depth] unit vectors used as random_in_unit_sphere()'s return values
+ *                     (sphere.c:19-24).  The reference draws them from the serial rand() stream; fed with
+ *                     the reference's own samples the frame is bit-identical to the reference's.
+ *   samples == NULL : counter-based generator keyed by (seed, pixel, depth); same rejection loop. */
+int gpu_render_frame(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, int max_depth,
+                     uint64_t seed, const Vec3 *samples, uint8_t *rgba_out);
+int gpu_render_frame_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, int max_depth,
+                         uint64_t seed, const void *d_samples, void *d_rgba, void *stream);
+/* Running mean of main.c:368-405: frames = number of frames including this one; frames == 1 restarts
+ * (accum = colour/255, shown colour = the frame's own), otherwise accum += colour/255 and the shown colour
+ * is (Uint8)fmin(accum / frames * 255.0f, 255.0f).  accum: 3 floats per pixel. */
+int gpu_accumulate(float *accum, int frames, const uint8_t *rgba, int64_t n_pixels, uint8_t *avg_rgba);
+int gpu_accumulate_dev(void *d_accum, int frames, const void *d_rgba, int64_t n_pixels, void *d_avg_rgba, void *stream);
+/* Binary PPM (P6) of an RGBA8 frame, in place of SDL_RenderDrawPoint (main.c:376,402). 0 = ok. */
+int sahbvh_write_ppm(const char *path, const uint8_t *rgba, int width, int height);
+
 /* Instrumented trace (counts work per ray; slower; same hits). */
 int gpu_trace_closest_hit_stats(gpu_bvh *bvh, const void *d_rays, int64_t n, void *d_out, gpu_trace_stats *stats);
 int gpu_trace_primary_stats(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,

@@ -491,3 +491,76 @@ void orc_walk_counters(const orc_node *nodes, const orc_sphere *spheres, int n_s
     }
     out[0] = inner; out[1] = tests; out[2] = max_sp;
 }
+
+/* ------------------------------------------------------------------ renderer.c:21-76 + main.c:356-405
+ * trace_ray as a loop (the recursion's arithmetic in the recursion's order): per pixel, row-major, drawing
+ * from the serial rand() stream exactly when the reference does (one random_on_hemisphere per hit, before the
+ * recursive call).  samples (optional) records the unit vectors random_in_unit_sphere() returned,
+ * [pixel][max_depth] (unused slots zero), so that a parallel implementation can be fed the same draws. */
+static void sky_rgba(float dir_y, uint8_t *c)
+{
+    float t = 0.5f * (dir_y + 1.0f);
+    float r = (1.0f - t) * 255 + t * 128, g = (1.0f - t) * 255 + t * 178;
+    c[0] = (uint8_t)(int)r; c[1] = (uint8_t)(int)g; c[2] = 255; c[3] = 255;
+}
+
+void orc_render(const orc_node *nodes, const orc_sphere *spheres, int n_spheres, const orc_camera *cam,
+                int width, int height, int y0, int y1, int max_depth, int use_bvh, orc_vec3 *samples, uint8_t *rgba)
+{
+    float aspect = (float)width / (float)height;
+    for (int y = y0; y < y1; y++) {
+        for (int x = 0; x < width; x++) {
+            size_t pix = (size_t)(y - y0) * (size_t)width + (size_t)x;
+            float u = ((float)x / (float)width - 0.5f) * aspect;
+            float v = (float)y / (float)height - 0.5f;
+            orc_ray ray = orc_camera_ray(cam, u, -v, width, height);
+            uint8_t base[64][3], c[4] = {0, 0, 0, 255};
+            int k = 0;
+            if (samples) memset(samples + pix * (size_t)max_depth, 0, (size_t)max_depth * sizeof(orc_vec3));
+            for (int depth = max_depth;; depth--) {
+                if (depth <= 0) { c[0] = c[1] = c[2] = 0; c[3] = 255; break; }      /* renderer.c:23-24 */
+                orc_hit h;
+                if (use_bvh) orc_intersect(nodes, spheres, n_spheres, ray, &h);
+                else {
+                    h = MISS;
+                    float best = INFINITY;
+                    for (int i = 0; i < n_spheres; i++) {                            /* renderer.c:36-43 */
+                        orc_hit t;
+                        if (orc_ray_sphere(ray, &spheres[i], i, &t) && t.t < best) { best = t.t; h = t; }
+                    }
+                }
+                if (h.prim < 0) { sky_rgba(ray.direction.y, c); break; }             /* renderer.c:66-71 */
+                base[k][0] = spheres[h.prim].rgba[0]; base[k][1] = spheres[h.prim].rgba[1]; base[k][2] = spheres[h.prim].rgba[2];
+                orc_vec3 nrm = {h.nx, h.ny, h.nz};
+                orc_vec3 d = rnd_unit_dir();                                         /* renderer.c:51, sphere.c:26-32 */
+                if (samples) samples[pix * (size_t)max_depth + (size_t)k] = d;
+                if (!((double)v_dot(d, nrm) > 0.0)) d = v_scale(d, -1.0f);
+                ray.origin.x = h.px; ray.origin.y = h.py; ray.origin.z = h.pz;       /* renderer.c:54 */
+                ray.direction = d;
+                k++;
+            }
+            for (int j = k - 1; j >= 0; j--)                                         /* renderer.c:56-58 */
+                for (int ch = 0; ch < 3; ch++) c[ch] = (uint8_t)(int)((double)base[j][ch] + 0.5 * (double)c[ch]);
+            c[3] = 255;
+            memcpy(rgba + 4 * pix, c, 4);
+        }
+    }
+}
+
+/* main.c:368-405: frames = count including this frame; frames == 1 restarts */
+void orc_accumulate(float *accum, int frames, const uint8_t *rgba, int64_t n_pixels, uint8_t *avg)
+{
+    for (int64_t p = 0; p < n_pixels; p++) {
+        for (int ch = 0; ch < 3; ch++) {
+            float v = (float)rgba[4 * p + ch] / 255.0f;
+            if (frames <= 1) {
+                accum[3 * p + ch] = v;
+                avg[4 * p + ch] = rgba[4 * p + ch];
+            } else {
+                accum[3 * p + ch] += v;
+                avg[4 * p + ch] = (uint8_t)(int)(fmin(accum[3 * p + ch] / frames * 255.0f, 255.0f));
+            }
+        }
+        avg[4 * p + 3] = 255;
+    }
+}

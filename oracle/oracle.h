@@ -73,4 +73,9 @@ double orc_trace_brute(const orc_sphere *spheres, int n_spheres,
 void orc_walk_counters(const orc_node *nodes, const orc_sphere *spheres, int n_spheres,
                        const orc_ray *rays, int64_t n, int64_t out[3], orc_hit *hits_or_null);
 
+/* path loop + accumulation (renderer.c:21-76, main.c:356-405); serial rand() stream */
+void orc_render(const orc_node *nodes, const orc_sphere *spheres, int n_spheres, const orc_camera *cam,
+                int width, int height, int y0, int y1, int max_depth, int use_bvh, orc_vec3 *samples, uint8_t *rgba);
+void orc_accumulate(float *accum, int frames, const uint8_t *rgba, int64_t n_pixels, uint8_t *avg);
+
 #endif

@@ -150,6 +150,22 @@ class Oracle:
                                        C.c_int64(len(rays)), _ptr(out), C.c_int(threads))
         return out, sec
 
+    def render(self, nodes, spheres, n_spheres, cam, w, h, y0=0, y1=None, max_depth=5, use_bvh=True, want_samples=True):
+        """renderer.c:21-76 over rows [y0,y1): RGBA8 [pixels,4] and the random_in_unit_sphere() draws [pixels,max_depth,3]."""
+        y1 = h if y1 is None else y1
+        npix = (y1 - y0) * w
+        rgba = np.zeros((npix, 4), np.uint8)
+        samples = np.zeros((npix, max(max_depth, 1), 3), np.float32) if want_samples else None
+        self.lib.orc_render(_ptr(nodes) if nodes is not None else None, _ptr(spheres), C.c_int(n_spheres), _ptr(cam),
+                            C.c_int(w), C.c_int(h), C.c_int(y0), C.c_int(y1), C.c_int(max_depth), C.c_int(1 if use_bvh else 0),
+                            _ptr(samples) if want_samples else None, _ptr(rgba))
+        return rgba, (samples[:, :max_depth] if want_samples else None)
+
+    def accumulate(self, accum, frames, rgba):
+        avg = np.zeros_like(rgba)
+        self.lib.orc_accumulate(_ptr(accum), C.c_int(frames), _ptr(np.ascontiguousarray(rgba)), C.c_int64(len(rgba)), _ptr(avg))
+        return avg
+
     def walk_counters(self, nodes, spheres, n_spheres, rays, want_hits=False):
         rays = np.ascontiguousarray(rays)
         cnt = (C.c_int64 * 3)()
@@ -245,6 +261,19 @@ class RefLib:
         sec = self.lib.refh_trace_bvh(C.c_void_p(root), _ptr(spheres), _ptr(rays), C.c_int64(len(rays)),
                                       _ptr(out), C.c_int(threads))
         return out, sec
+
+    def render(self, cam, spheres, n_spheres, root):
+        """The reference's own main.c:356-366 loop over trace_ray at this build's WIDTH x HEIGHT; root=None -> brute force."""
+        w, h = self.layout[17], self.layout[18]
+        rgba = np.zeros((w * h, 4), np.uint8)
+        self.lib.refh_render(_ptr(cam), _ptr(spheres), C.c_int(n_spheres), C.c_void_p(root) if root else None, _ptr(rgba))
+        return rgba
+
+    def accumulate(self, accum, frames, rgba, first):
+        """main.c:368-405; frames is a 1-element int32 array updated in place."""
+        shown = np.zeros_like(rgba)
+        self.lib.refh_accumulate(_ptr(accum), _ptr(frames), _ptr(np.ascontiguousarray(rgba)), C.c_int(1 if first else 0), _ptr(shown))
+        return shown
 
     def trace_brute(self, spheres, n_spheres, rays, threads=0):
         threads = threads or (os.cpu_count() or 1)

@@ -318,3 +318,44 @@ double refh_trace_brute(Sphere *base, int n_spheres, const Ray *rays, int64_t n,
 /* the two timed loops exactly as the reference runs them (clock(), rand() inside) */
 double refh_benchmark_no_bvh(Sphere *spheres, int n, int rays) { return benchmark_no_bvh(spheres, n, rays); }
 double refh_benchmark_with_bvh(BVHNode *root, int n, int rays) { return benchmark_with_bvh(root, n, rays); }
+
+/* ---- the reference's own path loop: main.c:356-366 calling trace_ray (renderer.c:21) with MAX_DEPTH, at this
+ * build's compile-time WIDTH x HEIGHT; rgba = SDL_Color bytes per pixel, row-major y*WIDTH+x ---- */
+#include "Custom/renderer.h"
+void refh_render(Camera *cam, Sphere *spheres, int n_spheres, BVHNode *root, unsigned char *rgba)
+{
+    float aspect_ratio = (float)WIDTH / (float)HEIGHT;
+    for (int y = 0; y < HEIGHT; y++) {
+        for (int x = 0; x < WIDTH; x++) {
+            float u = ((float)x / WIDTH - 0.5f) * aspect_ratio;
+            float v = (float)y / HEIGHT - 0.5f;
+            Ray ray = get_camera_ray(cam, u, -v);
+            SDL_Color color = trace_ray(ray, spheres, n_spheres, MAX_DEPTH, root);
+            unsigned char *o = rgba + 4 * ((size_t)y * WIDTH + x);
+            o[0] = color.r; o[1] = color.g; o[2] = color.b; o[3] = color.a;
+        }
+    }
+}
+
+/* main.c:368-405 verbatim on flat arrays (accum[pixel][3]); first != 0 is the camera.move branch */
+void refh_accumulate(float *accum, int *frames, const unsigned char *rgba, int first, unsigned char *shown)
+{
+    if (first) *frames = 1; else (*frames)++;
+    int accumulated_frames = *frames;
+    for (size_t p = 0; p < (size_t)WIDTH * HEIGHT; p++) {
+        SDL_Color color = {rgba[4 * p], rgba[4 * p + 1], rgba[4 * p + 2], rgba[4 * p + 3]};
+        float *a = accum + 3 * p;
+        if (first) {
+            a[0] = (float)color.r / 255.0f; a[1] = (float)color.g / 255.0f; a[2] = (float)color.b / 255.0f;
+            shown[4 * p] = color.r; shown[4 * p + 1] = color.g; shown[4 * p + 2] = color.b; shown[4 * p + 3] = color.a;
+        } else {
+            a[0] += (float)color.r / 255.0f; a[1] += (float)color.g / 255.0f; a[2] += (float)color.b / 255.0f;
+            SDL_Color avg_color = {
+                (Uint8)(fmin(a[0] / accumulated_frames * 255.0f, 255.0f)),
+                (Uint8)(fmin(a[1] / accumulated_frames * 255.0f, 255.0f)),
+                (Uint8)(fmin(a[2] / accumulated_frames * 255.0f, 255.0f)),
+                255};
+            shown[4 * p] = avg_color.r; shown[4 * p + 1] = avg_color.g; shown[4 * p + 2] = avg_color.b; shown[4 * p + 3] = avg_color.a;
+        }
+    }
+}

@@ -325,3 +325,12 @@ def test_scalar_primitives_match_oracle(pkg, oracle):
             w = np.array([want["t"][0], *want["p"][0], *want["n"][0]], np.float32)
             assert got.tobytes() == w.tobytes()
     assert agree > 100
+
+
+def test_write_ppm(pkg, tmp_path):
+    rgba = (np.arange(7 * 5 * 4) % 251).astype(np.uint8).reshape(-1, 4)
+    path = str(tmp_path / "frame.ppm")
+    pkg.write_ppm(path, rgba, 7, 5)
+    data = open(path, "rb").read()
+    assert data.startswith(b"P6\n7 5\n255\n")
+    assert data[len(b"P6\n7 5\n255\n"):] == rgba[:, :3].tobytes()

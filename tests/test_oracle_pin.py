@@ -166,3 +166,35 @@ def test_oracle_random_scenes_equal_reference_live(oracle, reflib):
         bo = oracle.bounce_rays(ho)
         assert same(br, bo)
         reflib.free(root)
+
+
+def test_oracle_path_loop_equals_reference_trace_ray(oracle, reflib):
+    """renderer.c:21-76 + main.c:356-366: the oracle's loop form of trace_ray == the reference's recursion, same
+    rand() stream, 800x600, MAX_DEPTH 5, BVH and brute-force branches; and the accumulation of main.c:368-405."""
+    cam = oracle.default_camera()
+    for seed, n in ((1, 20), (7, 60)):
+        reflib.srand(seed)
+        s = reflib.scene_random(n)
+        so = s.copy()
+        root, _ = reflib.build(s, 0, n, 0)
+        nodes = oracle.build(so, 0, n, 0)
+        assert same(s, so)
+        frames_ref, frames = [], []
+        for rep in range(3):
+            reflib.srand(100 + rep)
+            frames_ref.append(reflib.render(cam, s, n, root if rep != 1 else None))
+            oracle.srand(100 + rep)
+            got, samples = oracle.render(nodes, so, n, cam, 800, 600, use_bvh=(rep != 1))
+            frames.append(got)
+            assert same(got, frames_ref[-1]), f"seed {seed} frame {rep}"
+            assert (np.abs(np.linalg.norm(samples[samples.any(axis=2)], axis=1) - 1) < 1e-6).all()
+        assert len(np.unique(frames[0], axis=0)) > 50 and (frames[0] != frames[2]).any()
+        # accumulation
+        acc_r = np.zeros((800 * 600, 3), np.float32)
+        acc_o = np.zeros((800 * 600, 3), np.float32)
+        nfr = np.zeros(1, np.int32)
+        for k, f in enumerate(frames):
+            shown_r = reflib.accumulate(acc_r, nfr, f, first=(k == 0))
+            shown_o = oracle.accumulate(acc_o, k + 1, f)
+            assert same(shown_r, shown_o) and same(acc_r, acc_o) and int(nfr[0]) == k + 1
+        reflib.free(root)
