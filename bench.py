@@ -62,56 +62,74 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region.  The timed region is a few milliseconds long, so the
+    sampler polls NVML from a thread every ~1 ms (nvidia-smi -lms cannot go below ~100 ms); it falls back to one
+    nvidia-smi query taken while a kernel loop is still in flight when NVML is unavailable."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), int(mask)))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.h is None:
+            return self._smi_once()
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return self._smi_once()
+        reasons = set()
+        for _, mask in self.samples:
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([m for m, _ in self.samples])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(self.samples), "how": "NVML polled every ~1 ms during the timed steps"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            f = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [nm for k, nm in enumerate(names) if f[2 + k].lower().startswith("active")]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "reasons": reasons, "samples": 1,
+                    "how": "one nvidia-smi query right after the timed steps (NVML polling unavailable)"}
+        except Exception as e:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"no samples: {e}"]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -270,9 +288,10 @@ def run_b200(args):
     n_local = rows * W
     total_rays = W * H
     hits_local = torch.empty((n_local, 8), dtype=torch.float32, device="cuda")          # this rank's 32-byte records
-    # frame assembly (N > 1): all_gather of the compact {t, prim} ID buffer; the kernel writes this
-    # rank's band straight into its slot; double-buffered so gather k overlaps kernel k+1
-    ids = [torch.empty((world, n_local, 2), dtype=torch.float32, device="cuda") for _ in range(2)] if dist_on else None
+    # frame assembly (N > 1): all_gather of the 4-byte primitive-id buffer (t, point, normal are pure functions of
+    # the pixel's ray and the hit sphere: gpu_hits_from_prims_dev rebuilds bit-identical records wherever they are
+    # needed); the kernel writes this rank's band straight into its slot; double-buffered so gather k overlaps kernel k+1
+    ids = [torch.empty((world, n_local), dtype=torch.int32, device="cuda") for _ in range(2)] if dist_on else None
     comm = torch.cuda.Stream() if dist_on else None
 
     def run_steps(k_steps):
@@ -285,12 +304,12 @@ def run_b200(args):
                 buf = ids[k & 1]
                 if gather_done[k & 1] is not None:
                     main_stream.wait_event(gather_done[k & 1])
-                bvh.trace_primary_dev_ids(cam, W, H, y0, y1, hits_local.data_ptr(), buf[rank].data_ptr(), stream)
+                bvh.trace_primary_dev_prims(cam, W, H, y0, y1, hits_local.data_ptr(), buf[rank].data_ptr(), stream)
                 ek = torch.cuda.Event()
                 ek.record(main_stream)
                 with torch.cuda.stream(comm):
                     comm.wait_event(ek)
-                    dist.all_gather_into_tensor(buf.view(world * n_local, 2), buf[rank])
+                    dist.all_gather_into_tensor(buf.view(world * n_local), buf[rank])
                     gd = torch.cuda.Event()
                     gd.record(comm)
                     gather_done[k & 1] = gd
@@ -316,6 +335,22 @@ def run_b200(args):
     fence()
     launches = pkg.kernel_launches() - launches0
     clk = clocks.stop()
+    assembled_ok = None
+    if dist_on:
+        # untimed check of the assembled frame: the records rebuilt from the gathered ids of the NEXT rank's band must
+        # equal what that rank traced (exchanged here through one more all_gather of a 64 K-pixel sample)
+        nxt = (rank + 1) % world
+        ny0, ny1 = pkg.shard_rows(H, nxt, world)
+        rebuilt = torch.empty((n_local, 8), dtype=torch.float32, device="cuda")
+        bvh.hits_from_prims_dev(cam, W, H, ny0, ny1, ids[(args.steps - 1) & 1][nxt].data_ptr(), rebuilt.data_ptr(), stream)
+        torch.cuda.synchronize()
+        m = min(n_local, 1 << 16)
+        sample = [torch.empty((m, 8), dtype=torch.float32, device="cuda") for _ in range(world)]
+        dist.all_gather(sample, hits_local[:m].contiguous())
+        ok = bool((sample[nxt].view(torch.int32) == rebuilt[:m].view(torch.int32)).all().item())
+        tok = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(tok, op=dist.ReduceOp.MIN)
+        assembled_ok = bool(tok.item())
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if dist_on:
@@ -417,11 +452,11 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.spheres} random spheres (benchmark.c:306-314 recipe, srand 1), SAH BVH build(0,n,0), "
                                f"{W}x{H} primary rays of the default camera, closest hit, 32 B hit record per ray",
-                   "rays_per_step": total_rays, "rays_per_gpu": n_local, "bvh": info, "build_seconds_host": build_s,
+                   "rays_per_step": total_rays, "rays_per_gpu": n_local, "bvh": info, "build_seconds": build_s,
                    "l2": "160 MiB device memset before every timed step (inside the timed region, ~25 us)",
                    "timing": "one CUDA-event pair around the K steps on the launch stream, max over ranks",
                    "parallelism": f"rays sharded in {world} contiguous row band(s), BVH replicated" +
-                                  (", NCCL all_gather of the {t,prim} frame ID buffer (8 B/pixel) on a side stream, "
+                                  (", NCCL all_gather of the frame's primitive-id buffer (4 B/pixel) on a side stream, "
                                    "double-buffered so gather k overlaps kernel k+1; the kernel writes each rank's band "
                                    "straight into its all_gather slot" if dist_on else "")},
         "clocks": clk,
@@ -432,6 +467,9 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "sweep": sweep,
     }
+    if assembled_ok is not None:
+        line["config"]["assembled_frame_check"] = ("records rebuilt from the gathered ids == the owning rank's traced records "
+                                                   "(bit-exact, 64 K-pixel sample per rank): " + ("pass" if assembled_ok else "FAIL"))
     print(json.dumps(line), flush=True)
     if dist_on:
         dist.barrier()

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
     "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
     "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree",
-    "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
+    "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
@@ -336,6 +336,19 @@ class GpuBvh:
         _check(lib.gpu_trace_primary_dev_ids(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
                                              C.c_void_p(d_out), C.c_void_p(d_ids), C.c_void_p(stream)),
                "gpu_trace_primary_dev_ids")
+
+    def trace_primary_dev_prims(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_out: int, d_prims: int,
+                                stream: int = 0):
+        """Full records to d_out and the 4-byte primitive-id buffer to d_prims (the all-gather slot)."""
+        _check(lib.gpu_trace_primary_dev_prims(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                               C.c_void_p(d_out), C.c_void_p(d_prims), C.c_void_p(stream)),
+               "gpu_trace_primary_dev_prims")
+
+    def hits_from_prims_dev(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_prims: int, d_out: int,
+                            stream: int = 0):
+        _check(lib.gpu_hits_from_prims_dev(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                           C.c_void_p(d_prims), C.c_void_p(d_out), C.c_void_p(stream)),
+               "gpu_hits_from_prims_dev")
 
     def trace_closest_hit_stats(self, d_rays: int, n: int, d_out: int) -> dict:
         st = TraceStats()

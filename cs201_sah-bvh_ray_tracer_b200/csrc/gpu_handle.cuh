@@ -64,6 +64,6 @@ SahScene sahbvh_make_scene(const gpu_bvh_info &info);
 void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c);
 int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count);
 int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
-                          cudaStream_t st, bool count, void *d_ids);
+                          cudaStream_t st, bool count, void *d_ids, int ids_prim_only);
 
 #endif

@@ -249,7 +249,7 @@ extern "C" int gpu_render_frame_dev(gpu_bvh *b, const Camera *cam, int width, in
         if (rc != SAHBVH_OK) break;
         SahCamera c;
         sahbvh_make_camera(cam, width, height, &c);
-        rc = sahbvh_launch_primary(b, cam, width, height, y0, y1, rb.hits, st, false, nullptr);
+        rc = sahbvh_launch_primary(b, cam, width, height, y0, y1, rb.hits, st, false, nullptr, 0);
         if (rc != SAHBVH_OK) break;
         long long n_rays = n_pixels;
         int cur = 0;

@@ -354,7 +354,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(PRIMARY_THREADS)
 k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                 SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
-                unsigned long long *counters)
+                int ids_prim_only, unsigned long long *counters)
 {
     int32_t stack[SAH_STACK_MAX];
     SahCounters cnt = {0, 0, 0, 0};
@@ -371,7 +371,10 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
         sah_trace_one<COUNT>(nodes, spheres4, sc.n_spheres, r, stack, 1, h, &cnt);
         const size_t pix = (size_t)(y - y0) * (size_t)width + (size_t)x;
         store_hit(out + pix, h);
-        if (ids) ids[pix] = make_float2(h.t, __int_as_float(h.prim));
+        if (ids) {
+            if (ids_prim_only) reinterpret_cast<int32_t *>(ids)[pix] = h.prim;
+            else ids[pix] = make_float2(h.t, __int_as_float(h.prim));
+        }
         if (COUNT) hits += (h.prim >= 0);
     }
     if (COUNT) flush_counters(cnt, hits, counters);
@@ -405,7 +408,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(PKT_WARPS * 32)
 k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                        SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
-                       unsigned long long *counters)
+                       int ids_prim_only, unsigned long long *counters)
 {
     __shared__ int32_t s_stack[PKT_WARPS][PKT_STACK];
     const unsigned full = 0xffffffffu;
@@ -558,7 +561,10 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
             }
             const size_t pix = (size_t)(py[k] - y0) * (size_t)width + (size_t)px[k];
             store_hit(out + pix, h);
-            if (ids) ids[pix] = make_float2(h.t, __int_as_float(h.prim));
+            if (ids) {
+            if (ids_prim_only) reinterpret_cast<int32_t *>(ids)[pix] = h.prim;
+            else ids[pix] = make_float2(h.t, __int_as_float(h.prim));
+        }
         }
     }
     if (COUNT) flush_counters(cnt, hits, counters);
@@ -976,7 +982,7 @@ void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c)
 }
 
 int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
-                          cudaStream_t st, bool count, void *d_ids)
+                          cudaStream_t st, bool count, void *d_ids, int ids_prim_only)
 {
     if (y1 <= y0 || width <= 0) return SAHBVH_OK;
     SahCamera c;
@@ -989,18 +995,18 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
         unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
         if (count)
             k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
-                                                                         out, ids, b->d_counters);
+                                                                         out, ids, ids_prim_only, b->d_counters);
         else
             k_trace_primary_packet<false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
-                                                                          out, ids, nullptr);
+                                                                          out, ids, ids_prim_only, nullptr);
     } else {
         dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
         if (count)
             k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
-                                                                   out, ids, b->d_counters);
+                                                                   out, ids, ids_prim_only, b->d_counters);
         else
             k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
-                                                                    out, ids, nullptr);
+                                                                    out, ids, ids_prim_only, nullptr);
     }
     g_launches++;
     CU_TRY(cudaGetLastError());
@@ -1083,7 +1089,7 @@ extern "C" int gpu_trace_primary_dev(gpu_bvh *b, const Camera *cam, int width, i
     int rc = check_frame(b, cam, width, height, y0, y1, d_out);
     if (rc != SAHBVH_OK) return rc;
     DeviceGuard guard(b->device);
-    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, nullptr);
+    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, nullptr, 0);
 }
 
 extern "C" int gpu_trace_primary_dev_ids(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
@@ -1092,7 +1098,62 @@ extern "C" int gpu_trace_primary_dev_ids(gpu_bvh *b, const Camera *cam, int widt
     int rc = check_frame(b, cam, width, height, y0, y1, d_out);
     if (rc != SAHBVH_OK) return rc;
     DeviceGuard guard(b->device);
-    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_ids);
+    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_ids, 0);
+}
+
+extern "C" int gpu_trace_primary_dev_prims(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
+                                           void *d_out, void *d_prims, void *stream)
+{
+    int rc = check_frame(b, cam, width, height, y0, y1, d_out);
+    if (rc != SAHBVH_OK) return rc;
+    DeviceGuard guard(b->device);
+    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_prims, 1);
+}
+
+/* prim ids of image rows -> full hit records: t, point and normal are pure functions of the pixel's ray and the
+ * hit sphere (hit.c:19-39 evaluated once more on the winner), so the result is bit-identical to the traced record */
+__global__ void __launch_bounds__(PRIMARY_THREADS)
+k_hits_from_prims(const float *__restrict__ spheres4, SahScene sc, SahCamera cam, int width, int y0, int y1,
+                  const int32_t *__restrict__ prims, gpu_hit *__restrict__ out)
+{
+    const long long pix = (long long)blockIdx.x * PRIMARY_THREADS + threadIdx.x;
+    if (pix >= (long long)(y1 - y0) * width) return;
+    SahHit h;
+    sah_miss(h);
+    const int32_t prim = prims[pix];
+    if (prim >= 0 && prim < sc.n_spheres) {
+        float dx, dy, dz;
+        sah_primary_dir(cam, (int)(pix % width), y0 + (int)(pix / width), dx, dy, dz);
+        SahRay r;
+        r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
+        r.dx = dx; r.dy = dy; r.dz = dz;
+        r.a = F_ADD(F_ADD(F_MUL(dx, dx), F_MUL(dy, dy)), F_MUL(dz, dz));
+        const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + prim);
+        float t;
+        if (sah_sphere_t(r, s.x, s.y, s.z, s.w, t)) sah_finish_hit(r, t, prim, s.x, s.y, s.z, h);
+    }
+    store_hit(out + pix, h);
+}
+
+extern "C" int gpu_hits_from_prims_dev(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
+                                       const void *d_prims, void *d_out, void *stream)
+{
+    int rc = check_frame(b, cam, width, height, y0, y1, d_out);
+    if (rc != SAHBVH_OK) return rc;
+    if (!d_prims) {
+        sahbvh_set_error("gpu_hits_from_prims_dev: NULL prims");
+        return SAHBVH_E_ARG;
+    }
+    if (y1 == y0) return SAHBVH_OK;
+    DeviceGuard guard(b->device);
+    SahCamera c;
+    sahbvh_make_camera(cam, width, height, &c);
+    const long long n = (long long)(y1 - y0) * width;
+    k_hits_from_prims<<<(unsigned)((n + PRIMARY_THREADS - 1) / PRIMARY_THREADS), PRIMARY_THREADS, 0, (cudaStream_t)stream>>>(
+        b->d_spheres4, sahbvh_make_scene(b->info), c, width, y0, y1, (const int32_t *)d_prims, (gpu_hit *)d_out);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return SAHBVH_OK;
 }
 
 extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out)
@@ -1111,7 +1172,7 @@ extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int h
     for (int ya = y0; ya < y1; ya += band, k ^= 1) {
         int yb = ya + band < y1 ? ya + band : y1;
         cudaStream_t st = b->streams[k];
-        rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false, nullptr);
+        rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false, nullptr, 0);
         if (rc != SAHBVH_OK) return rc;
         CU_TRY(cudaMemcpyAsync(out + (size_t)(ya - y0) * (size_t)width, b->d_out[k],
                                (size_t)(yb - ya) * (size_t)width * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
@@ -1280,7 +1341,7 @@ extern "C" int gpu_trace_primary_stats(gpu_bvh *b, const Camera *cam, int width,
     if (!stats) return SAHBVH_E_ARG;
     DeviceGuard guard(b->device);
     CU_TRY(cudaMemset(b->d_counters, 0, 8 * sizeof(unsigned long long)));
-    rc = sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, 0, true, nullptr);
+    rc = sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, 0, true, nullptr, 0);
     if (rc != SAHBVH_OK) return rc;
     CU_TRY(cudaDeviceSynchronize());
     return read_counters(b, (uint64_t)(y1 - y0) * (uint64_t)width, stats);

@@ -118,6 +118,14 @@ int gpu_trace_primary_dev(gpu_bvh *bvh, const Camera *cam, int width, int height
  * straight into its slot of the all-gather buffer, so no pack/copy kernel sits between them. */
 int gpu_trace_primary_dev_ids(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
                               void *d_out, void *d_ids, void *stream);
+/* The 4-byte variant: d_prims receives only the int32 primitive id per pixel (-1 = miss).  t, point and normal
+ * are pure functions of the pixel's ray and the hit sphere, so gpu_hits_from_prims_dev rebuilds the full,
+ * bit-identical 32-byte records from the ids on whichever GPU needs them: the multi-GPU frame assembly
+ * gathers 4 bytes per pixel over NVLink instead of 32. */
+int gpu_trace_primary_dev_prims(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
+                                void *d_out, void *d_prims, void *stream);
+int gpu_hits_from_prims_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
+                            const void *d_prims, void *d_out, void *stream);
 /* Which kernel gpu_trace_primary* launches (process-wide; both give identical hit records):
  *   SAHBVH_PRIMARY_PACKET  (default) one warp per 16x8 pixel tile, interior culling once per tile
  *   SAHBVH_PRIMARY_PER_RAY one thread per pixel, per-ray stack traversal (the ray-buffer kernel's core) */

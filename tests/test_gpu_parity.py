@@ -603,3 +603,23 @@ def test_render_frame_generated_samples_and_accumulation(gpu, oracle):
         shown_o = oracle.accumulate(acc_o, k + 1, f)
         assert same(shown_g, shown_o) and same(acc_g, acc_o)
     bvh.close()
+
+
+def test_hits_rebuilt_from_primitive_ids(gpu, oracle, scene100k):
+    """Multi-GPU frame assembly gathers 4-byte primitive ids; gpu_hits_from_prims_dev must rebuild the exact records."""
+    import torch
+    bvh, s, _, nodes = scene100k
+    cam = gpu.default_camera()
+    for (w, h, y0, y1) in ((3840, 2160, 0, 2160), (1023, 517, 5, 412)):
+        n = (y1 - y0) * w
+        d_hits = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+        d_prims = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+        d_back = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        bvh.trace_primary_dev_prims(cam, w, h, y0, y1, d_hits.data_ptr(), d_prims.data_ptr(), st)
+        bvh.hits_from_prims_dev(cam, w, h, y0, y1, d_prims.data_ptr(), d_back.data_ptr(), st)
+        torch.cuda.synchronize()
+        hits = d_hits.cpu().numpy().view(HIT_DT).reshape(-1)
+        assert same(hits["prim"], d_prims.cpu().numpy())
+        assert_hits_equal(d_back.cpu().numpy().view(HIT_DT).reshape(-1), hits, f"rebuilt from ids {w}x{h}")
+        assert (hits["prim"] >= 0).sum() > 100
