@@ -391,7 +391,13 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
  */
 #define PKT_WARPS 4
 #define PKT_STACK 512
-#define PKT_K 4
+#ifndef PKT_K
+#define PKT_K 4 /* rays per lane: tile = 16 x (2*PKT_K) pixels */
+#endif
+#define PKT_TILE_H (2 * PKT_K)
+#ifndef PKT_MIN_BLOCKS
+#define PKT_MIN_BLOCKS 8
+#endif
 
 __device__ __forceinline__ float warp_min(float v)
 {
@@ -405,42 +411,48 @@ __device__ __forceinline__ float warp_max(float v)
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(PKT_WARPS * 32)
+__global__ void __launch_bounds__(PKT_WARPS * 32, PKT_MIN_BLOCKS)
 k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                        SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
                        int ids_prim_only, unsigned long long *counters)
 {
+    /* The traversal loop is a chain of dependent node fetches, so it needs resident warps more than registers:
+     * the per-ray state (direction, d.d, best t, best index of the lane's 4 rays) lives in shared memory -- it is
+     * only touched when a candidate leaf is tested (about 5 times per tile) -- which leaves ~56 registers per
+     * thread and 10 CTAs (40 warps) per SM instead of 5. */
     __shared__ int32_t s_stack[PKT_WARPS][PKT_STACK];
+    __shared__ float s_ray[PKT_WARPS][PKT_K][4][32];   /* dx, dy, dz, d.d */
+    __shared__ float s_bt[PKT_WARPS][PKT_K][32];
+    __shared__ int32_t s_bp[PKT_WARPS][PKT_K][32];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_x = (width + 15) >> 4, tiles_y = (y1 - y0 + 7) >> 3;
+    const int tiles_x = (width + 15) >> 4, tiles_y = (y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H;
     const long long tile = (long long)blockIdx.x * PKT_WARPS + warp;
     SahCounters cnt = {0, 0, 0, 0};
     unsigned long long hits = 0;
     if (tile < (long long)tiles_x * tiles_y) {
         int32_t *stack = s_stack[warp];
         const int tx = (int)(tile % tiles_x), ty = (int)(tile / tiles_x);
-        /* ---- this lane's 4 rays ---- */
-        float dx[PKT_K], dy[PKT_K], dz[PKT_K], ra[PKT_K], best_t[PKT_K];
-        int32_t best_p[PKT_K];
-        bool valid[PKT_K];
-        int px[PKT_K], py[PKT_K];
+        /* ---- this lane's 4 rays: pixel (tx*16 + (k&1)*8 + lane%8, y0 + ty*8 + (k>>1)*4 + lane/8) ---- */
+        const int px0 = tx * 16 + (lane & 7), py0 = y0 + ty * PKT_TILE_H + (lane >> 3);
+        unsigned valid = 0;
         float lminx = INFINITY, lminy = INFINITY, lminz = INFINITY, lmaxx = -INFINITY, lmaxy = -INFINITY, lmaxz = -INFINITY;
         float lmin_a = INFINITY;
 #pragma unroll
         for (int k = 0; k < PKT_K; k++) {
-            px[k] = tx * 16 + (k & 1) * 8 + (lane & 7);
-            py[k] = y0 + ty * 8 + (k >> 1) * 4 + (lane >> 3);
-            valid[k] = px[k] < width && py[k] < y1;
-            sah_primary_dir(cam, px[k], py[k], dx[k], dy[k], dz[k]);
-            ra[k] = F_ADD(F_ADD(F_MUL(dx[k], dx[k]), F_MUL(dy[k], dy[k])), F_MUL(dz[k], dz[k]));
-            best_t[k] = 0.0f;
-            best_p[k] = -1;
-            if (valid[k]) {
-                lminx = fminf(lminx, dx[k]); lmaxx = fmaxf(lmaxx, dx[k]);
-                lminy = fminf(lminy, dy[k]); lmaxy = fmaxf(lmaxy, dy[k]);
-                lminz = fminf(lminz, dz[k]); lmaxz = fmaxf(lmaxz, dz[k]);
-                lmin_a = fminf(lmin_a, ra[k]);
+            const int px = px0 + (k & 1) * 8, py = py0 + (k >> 1) * 4;
+            float dx, dy, dz;
+            sah_primary_dir(cam, px, py, dx, dy, dz);
+            const float ra = F_ADD(F_ADD(F_MUL(dx, dx), F_MUL(dy, dy)), F_MUL(dz, dz));
+            s_ray[warp][k][0][lane] = dx; s_ray[warp][k][1][lane] = dy; s_ray[warp][k][2][lane] = dz; s_ray[warp][k][3][lane] = ra;
+            s_bt[warp][k][lane] = 0.0f;
+            s_bp[warp][k][lane] = -1;
+            if (px < width && py < y1) {
+                valid |= 1u << k;
+                lminx = fminf(lminx, dx); lmaxx = fmaxf(lmaxx, dx);
+                lminy = fminf(lminy, dy); lmaxy = fmaxf(lmaxy, dy);
+                lminz = fminf(lminz, dz); lmaxz = fmaxf(lmaxz, dz);
+                lmin_a = fminf(lmin_a, ra);
             }
         }
         lminx = warp_min(lminx); lminy = warp_min(lminy); lminz = warp_min(lminz);
@@ -502,34 +514,35 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                 const int32_t sidx = ~__shfl_sync(full, ref, src);
                 const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + sidx);
                 float tt[PKT_K];
-                bool need = false, needk[PKT_K];
+                unsigned needk = 0;
 #pragma unroll
                 for (int k = 0; k < PKT_K; k++) {
-                    SahRay r;
-                    r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
-                    r.dx = dx[k]; r.dy = dy[k]; r.dz = dz[k];
-                    r.a = ra[k];
-                    needk[k] = false;
-                    if (valid[k]) {
+                    if (valid & (1u << k)) {
+                        SahRay r;
+                        r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
+                        r.dx = s_ray[warp][k][0][lane]; r.dy = s_ray[warp][k][1][lane]; r.dz = s_ray[warp][k][2][lane];
+                        r.a = s_ray[warp][k][3][lane];
                         if (COUNT) cnt.spheres++;
-                        if (sah_sphere_t(r, s.x, s.y, s.z, s.w, tt[k]))
-                            needk[k] = best_p[k] < 0 || tt[k] < best_t[k] || (tt[k] == best_t[k] && sidx > best_p[k]);
+                        if (sah_sphere_t(r, s.x, s.y, s.z, s.w, tt[k])) {
+                            const float bt = s_bt[warp][k][lane];
+                            const int32_t bp = s_bp[warp][k][lane];
+                            if (bp < 0 || tt[k] < bt || (tt[k] == bt && sidx > bp)) needk |= 1u << k;
+                        }
                     }
-                    need |= needk[k];
                 }
-                if (__any_sync(full, need)) {
+                if (__any_sync(full, needk != 0)) {
                     const float blx = __shfl_sync(full, lox, src), bly = __shfl_sync(full, loy, src), blz = __shfl_sync(full, loz, src);
                     const float bhx = __shfl_sync(full, hix, src), bhy = __shfl_sync(full, hiy, src), bhz = __shfl_sync(full, hiz, src);
 #pragma unroll
                     for (int k = 0; k < PKT_K; k++) {
-                        if (needk[k]) {
+                        if (needk & (1u << k)) {
                             SahRay r;
                             r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
-                            r.dx = dx[k]; r.dy = dy[k]; r.dz = dz[k];
+                            r.dx = s_ray[warp][k][0][lane]; r.dy = s_ray[warp][k][1][lane]; r.dz = s_ray[warp][k][2][lane];
                             if (COUNT) cnt.exact++;
                             if (sah_box_exact(r, blx, bly, blz, bhx, bhy, bhz)) {
-                                best_t[k] = tt[k];
-                                best_p[k] = sidx;
+                                s_bt[warp][k][lane] = tt[k];
+                                s_bp[warp][k][lane] = sidx;
                                 changed = true;
                             }
                         }
@@ -540,31 +553,34 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                 float w = 0.0f; /* worst (largest) cull bound over this lane's valid rays */
 #pragma unroll
                 for (int k = 0; k < PKT_K; k++)
-                    if (valid[k]) w = fmaxf(w, best_p[k] >= 0 ? F_FMA(best_t[k], SAH_REL_CULL, cull_abs) : INFINITY);
+                    if (valid & (1u << k))
+                        w = fmaxf(w, s_bp[warp][k][lane] >= 0 ? F_FMA(s_bt[warp][k][lane], SAH_REL_CULL, cull_abs) : INFINITY);
                 pkt_best_s = warp_max(w);
             }
         }
         /* ---- results ---- */
 #pragma unroll
         for (int k = 0; k < PKT_K; k++) {
-            if (!valid[k]) continue;
+            if (!(valid & (1u << k))) continue;
+            const int px = px0 + (k & 1) * 8, py = py0 + (k >> 1) * 4;
             SahHit h;
-            if (best_p[k] >= 0) {
+            const int32_t bp = s_bp[warp][k][lane];
+            if (bp >= 0) {
                 SahRay r;
                 r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
-                r.dx = dx[k]; r.dy = dy[k]; r.dz = dz[k];
-                const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + best_p[k]);
-                sah_finish_hit(r, best_t[k], best_p[k], s.x, s.y, s.z, h);
+                r.dx = s_ray[warp][k][0][lane]; r.dy = s_ray[warp][k][1][lane]; r.dz = s_ray[warp][k][2][lane];
+                const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + bp);
+                sah_finish_hit(r, s_bt[warp][k][lane], bp, s.x, s.y, s.z, h);
                 if (COUNT) hits++;
             } else {
                 sah_miss(h);
             }
-            const size_t pix = (size_t)(py[k] - y0) * (size_t)width + (size_t)px[k];
+            const size_t pix = (size_t)(py - y0) * (size_t)width + (size_t)px;
             store_hit(out + pix, h);
             if (ids) {
-            if (ids_prim_only) reinterpret_cast<int32_t *>(ids)[pix] = h.prim;
-            else ids[pix] = make_float2(h.t, __int_as_float(h.prim));
-        }
+                if (ids_prim_only) reinterpret_cast<int32_t *>(ids)[pix] = h.prim;
+                else ids[pix] = make_float2(h.t, __int_as_float(h.prim));
+            }
         }
     }
     if (COUNT) flush_counters(cnt, hits, counters);
@@ -991,7 +1007,7 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
     float2 *ids = (float2 *)d_ids;
     const SahScene sc = sahbvh_make_scene(b->info);
     if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
-        long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + 7) / 8);
+        long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H);
         unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
         if (count)
             k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
