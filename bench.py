@@ -401,8 +401,8 @@ def run_b200(args):
     model = algorithmic(stats_ray, generated=True, with_input=False)      # SURVEY 8(d) per-ray figure
     peaks = pkg.measure_peaks(local)
     k_s = k_ms * 1e-3
-    compulsory_bytes = 32 * n_local + info["n_inner"] * 64 + (info["n_spheres"] + 1) * 16
-    touched_bytes = 64 * stats["inner_visits"] + 16 * stats["sphere_tests"] + 32 * n_local
+    compulsory_bytes = 32 * n_local + info["n_wide"] * 128 + (info["n_spheres"] + 1) * 16
+    touched_bytes = 128 * stats["inner_visits"] + 16 * stats["sphere_tests"] + 32 * n_local   # 128-byte 4-wide nodes
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -414,7 +414,7 @@ def run_b200(args):
         "frac": compulsory_bytes / k_s / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": compulsory_bytes,
         "what": "compulsory HBM bytes of one launch: 32 B hit record per ray written once + the flattened tree "
-                "(64 B/inner node, 16 B/sphere) read once; the ncu profile shows the kernel is instruction-issue bound, "
+                "(128 B per 4-wide node, 16 B/sphere) read once; the ncu profile shows the kernel is instruction-issue bound, "
                 "not HBM bound (profiles/)",
         "kernel_ms": k_ms,
         "tile_work": {"tiles": tiles, "nodes_popped_per_tile": stats["inner_visits"] / tiles,

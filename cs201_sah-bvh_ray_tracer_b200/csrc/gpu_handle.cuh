@@ -16,6 +16,7 @@ struct gpu_bvh {
     uint32_t *d_colors;
     uint32_t *d_wide;   /* 4-wide quantised nodes (wide.c), 64 B each */
     float *d_special;   /* special-leaf records, 32 B each */
+    float *d_wide_full; /* full-precision twins of the wide nodes, 128 B each (packet kernel) */
     int n_wide, n_special;
     int wide_blocks_per_sm;
     unsigned long long *d_counters; /* [0..7] work counters, [8..71] per-launch ray cursors of the persistent kernel */

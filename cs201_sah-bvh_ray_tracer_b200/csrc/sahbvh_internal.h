@@ -51,6 +51,7 @@ typedef struct flat_bvh {
 
 typedef struct wide_bvh {
     uint32_t *nodes;   /* n_wide * 16 words, 64-byte aligned */
+    float *full;       /* n_wide * 32 floats: the same nodes with four full-precision 32-byte child records */
     float *special;    /* n_special * 8 floats: lo.xyz, hi.x, hi.y, hi.z, sphere index (bits), 0 */
     int32_t n_wide, n_special;
     int32_t max_depth;

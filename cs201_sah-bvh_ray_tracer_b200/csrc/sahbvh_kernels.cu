@@ -382,8 +382,9 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
 
 /*
  * K2p: packet traversal for primary rays.  One WARP owns a 16x8 pixel tile (4 rays per lane,
- * shared origin).  Interior culling is done ONCE PER TILE: the lanes test 32 child boxes of up
- * to 16 popped nodes in parallel against the tile's direction-interval frustum
+ * shared origin).  Interior culling is done ONCE PER TILE over the 4-wide tree (full-precision
+ * 128-byte nodes, wide.c): the lanes test the 32 child boxes of up
+ * to 8 popped nodes in parallel against the tile's direction-interval frustum
  * (sah_frustum_box), surviving inner children are pushed back in near-last order, surviving
  * leaves become candidates.  Every ray of the tile then runs the reference-exact sphere test
  * (and, for a would-be winner, the reference-exact leaf box test) on each candidate, so the
@@ -395,6 +396,10 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
 #define PKT_K 4 /* rays per lane: tile = 16 x (2*PKT_K) pixels */
 #endif
 #define PKT_TILE_H (2 * PKT_K)
+#ifndef PKT_UNROLL
+#define PKT_UNROLL 4 /* per-ray loops: rolled (1) measures the same within 1%; the state is in shared memory either way */
+#endif
+static constexpr int kPktUnroll = PKT_UNROLL;
 #ifndef PKT_MIN_BLOCKS
 #define PKT_MIN_BLOCKS 8
 #endif
@@ -424,6 +429,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
     __shared__ float s_ray[PKT_WARPS][PKT_K][4][32];   /* dx, dy, dz, d.d */
     __shared__ float s_bt[PKT_WARPS][PKT_K][32];
     __shared__ int32_t s_bp[PKT_WARPS][PKT_K][32];
+    __shared__ float s_tt[PKT_WARPS][PKT_K][32];       /* t of a would-be winner between the sphere and the box test */
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (width + 15) >> 4, tiles_y = (y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H;
@@ -438,7 +444,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
         unsigned valid = 0;
         float lminx = INFINITY, lminy = INFINITY, lminz = INFINITY, lmaxx = -INFINITY, lmaxy = -INFINITY, lmaxz = -INFINITY;
         float lmin_a = INFINITY;
-#pragma unroll
+#pragma unroll kPktUnroll
         for (int k = 0; k < PKT_K; k++) {
             const int px = px0 + (k & 1) * 8, py = py0 + (k >> 1) * 4;
             float dx, dy, dz;
@@ -476,9 +482,9 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
         if (lane == 0) stack[0] = 0;
         __syncwarp();
         while (top > 0) {
-            int npop = top < 16 ? top : 16;
-            if (top > PKT_STACK - 96) npop = 1; /* nearly full: plain DFS (growth <= tree depth) */
-            const int j = lane >> 1, c = lane & 1;
+            int npop = top < 8 ? top : 8;
+            if (top > PKT_STACK - 96) npop = 1; /* nearly full: plain DFS (growth <= 3 per level) */
+            const int j = lane >> 2, c = lane & 3;
             const bool active = j < npop;
             int32_t nd = active ? stack[top - 1 - j] : 0;
             __syncwarp();
@@ -486,21 +492,27 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
             if (COUNT && lane == 0) cnt.inner += (unsigned long long)npop;
             bool pass = false;
             float tn = INFINITY, lox = 0, loy = 0, loz = 0, hix = 0, hiy = 0, hiz = 0;
-            int32_t ref = 0;
+            int32_t ref = SAH_REF_NONE;
             if (active) {
-                const float4 *rec = reinterpret_cast<const float4 *>(nodes + (size_t)nd * 16 + c * 8);
+                /* 128-byte 4-wide node (wide.c, full-precision twin): lane (j, c) tests child c of popped node j */
+                const float4 *rec = reinterpret_cast<const float4 *>(nodes + (size_t)nd * 32 + c * 8);
                 float4 c0 = __ldg(rec), c1 = __ldg(rec + 1);
                 lox = c0.x; loy = c0.y; loz = c0.z; hix = c0.w; hiy = c1.x; hiz = c1.y;
                 ref = __float_as_int(c1.z);
-                pass = sah_frustum_box(FX, FY, FZ, lox, loy, loz, hix, hiy, hiz, pkt_best_s, tn);
+                pass = ref != SAH_REF_NONE && sah_frustum_box(FX, FY, FZ, lox, loy, loz, hix, hiy, hiz, pkt_best_s, tn);
             }
             const bool is_leaf = ref < 0;
             const bool push = pass && !is_leaf;
             const bool cand = pass && is_leaf && (uint32_t)(~ref) < (uint32_t)sc.n_spheres;
-            /* stack order: children of deeper stack entries first, of the top entry last; within a pair far first */
-            float tn_other = __shfl_xor_sync(full, tn, 1);
-            int is_near = (tn < tn_other || (tn == tn_other && c == 0)) ? 1 : 0;
-            int order = (15 - j) * 2 + is_near;
+            /* stack order: children of deeper stack entries first, of the top entry last; within a node far first,
+             * near last (rank among the four siblings by packet entry distance, ties by slot) */
+            int rank = 0;
+#pragma unroll
+            for (int x = 1; x < 4; x++) {
+                const float to = __shfl_xor_sync(full, tn, x);
+                rank += (to < tn || (to == tn && (c ^ x) < c)) ? 1 : 0;
+            }
+            const int order = (7 - j) * 4 + (3 - rank);
             unsigned ord_mask = __reduce_or_sync(full, push ? (1u << order) : 0u);
             if (push) stack[top + __popc(ord_mask & ((1u << order) - 1u))] = ref;
             top += __popc(ord_mask);
@@ -513,9 +525,8 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                 m &= m - 1;
                 const int32_t sidx = ~__shfl_sync(full, ref, src);
                 const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + sidx);
-                float tt[PKT_K];
                 unsigned needk = 0;
-#pragma unroll
+#pragma unroll kPktUnroll
                 for (int k = 0; k < PKT_K; k++) {
                     if (valid & (1u << k)) {
                         SahRay r;
@@ -523,17 +534,21 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                         r.dx = s_ray[warp][k][0][lane]; r.dy = s_ray[warp][k][1][lane]; r.dz = s_ray[warp][k][2][lane];
                         r.a = s_ray[warp][k][3][lane];
                         if (COUNT) cnt.spheres++;
-                        if (sah_sphere_t(r, s.x, s.y, s.z, s.w, tt[k])) {
+                        float t;
+                        if (sah_sphere_t(r, s.x, s.y, s.z, s.w, t)) {
                             const float bt = s_bt[warp][k][lane];
                             const int32_t bp = s_bp[warp][k][lane];
-                            if (bp < 0 || tt[k] < bt || (tt[k] == bt && sidx > bp)) needk |= 1u << k;
+                            if (bp < 0 || t < bt || (t == bt && sidx > bp)) {
+                                needk |= 1u << k;
+                                s_tt[warp][k][lane] = t;
+                            }
                         }
                     }
                 }
                 if (__any_sync(full, needk != 0)) {
                     const float blx = __shfl_sync(full, lox, src), bly = __shfl_sync(full, loy, src), blz = __shfl_sync(full, loz, src);
                     const float bhx = __shfl_sync(full, hix, src), bhy = __shfl_sync(full, hiy, src), bhz = __shfl_sync(full, hiz, src);
-#pragma unroll
+#pragma unroll kPktUnroll
                     for (int k = 0; k < PKT_K; k++) {
                         if (needk & (1u << k)) {
                             SahRay r;
@@ -541,7 +556,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                             r.dx = s_ray[warp][k][0][lane]; r.dy = s_ray[warp][k][1][lane]; r.dz = s_ray[warp][k][2][lane];
                             if (COUNT) cnt.exact++;
                             if (sah_box_exact(r, blx, bly, blz, bhx, bhy, bhz)) {
-                                s_bt[warp][k][lane] = tt[k];
+                                s_bt[warp][k][lane] = s_tt[warp][k][lane];
                                 s_bp[warp][k][lane] = sidx;
                                 changed = true;
                             }
@@ -559,7 +574,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
             }
         }
         /* ---- results ---- */
-#pragma unroll
+#pragma unroll kPktUnroll
         for (int k = 0; k < PKT_K; k++) {
             if (!(valid & (1u << k))) continue;
             const int px = px0 + (k & 1) * 8, py = py0 + (k >> 1) * 4;
@@ -775,6 +790,8 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
         if ((err = cudaMalloc(&b->d_counters, 72 * sizeof(unsigned long long))) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_wide, wide_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_special, special_bytes)) != cudaSuccess) break;
+        if ((err = cudaMalloc(&b->d_wide_full, wide_bytes * 2)) != cudaSuccess) break;
+        if ((err = cudaMemcpy(b->d_wide_full, wb.full, wide_bytes * 2, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_wide, wb.nodes, wide_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_special, wb.special, special_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_nodes, f->nodes, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
@@ -790,7 +807,7 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
         gpu_bvh_free(b);
         return SAHBVH_E_CUDA;
     }
-    b->info.device_bytes = (int64_t)(node_bytes + sph_bytes + col_bytes + wide_bytes + special_bytes);
+    b->info.device_bytes = (int64_t)(node_bytes + sph_bytes + col_bytes + 3 * wide_bytes + special_bytes);
     *out = b;
     return SAHBVH_OK;
 }
@@ -882,6 +899,7 @@ extern "C" void gpu_bvh_free(gpu_bvh *b)
     if (b->d_counters) cudaFree(b->d_counters);
     if (b->d_wide) cudaFree(b->d_wide);
     if (b->d_special) cudaFree(b->d_special);
+    if (b->d_wide_full) cudaFree(b->d_wide_full);
     if (b->d_render) cudaFree(b->d_render);
     free(b);
 }
@@ -1010,10 +1028,10 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
         long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H);
         unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
         if (count)
-            k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
+            k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                          out, ids, ids_prim_only, b->d_counters);
         else
-            k_trace_primary_packet<false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
+            k_trace_primary_packet<false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                           out, ids, ids_prim_only, nullptr);
     } else {
         dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);

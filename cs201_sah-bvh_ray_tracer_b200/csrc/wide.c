@@ -30,6 +30,10 @@
  * not quantisable).  The s/512 margin absorbs the rounding of the kernel's two FMAs per plane
  * (<= 2^-15 s, see traverse_core.cuh), so no run-time widening is needed.
  *
+ * Every node also gets a FULL-PRECISION twin (w->full, 128 bytes = four 32-byte child records in the binary
+ * tree's own format, boxes and leaf refs unchanged) with the same numbering: the packet kernel tests one child
+ * box per lane, so it gains the halved depth without paying for a decode.
+ *
  * Children are chosen by the usual surface-area greedy collapse: start from the two children of
  * a binary node and repeatedly open the inner child with the largest area until there are 4.
  */
@@ -146,10 +150,14 @@ static int32_t emit(ctx_t *c, int32_t b2, int depth)
     if (w->n_wide == c->cap_nodes) {
         int64_t ncap = c->cap_nodes * 2;
         uint32_t *nn = (uint32_t *)aligned_alloc(64, (size_t)ncap * 64);
-        if (!nn) { c->rc = SAHBVH_E_NOMEM; return SAHBVH_REF_NONE; }
+        float *nf = (float *)aligned_alloc(128, (size_t)ncap * 128);
+        if (!nn || !nf) { free(nn); free(nf); c->rc = SAHBVH_E_NOMEM; return SAHBVH_REF_NONE; }
         memcpy(nn, w->nodes, (size_t)w->n_wide * 64);
+        memcpy(nf, w->full, (size_t)w->n_wide * 128);
         free(w->nodes);
+        free(w->full);
         w->nodes = nn;
+        w->full = nf;
         c->cap_nodes = ncap;
     }
     const int32_t me = w->n_wide++;
@@ -174,6 +182,23 @@ static int32_t emit(ctx_t *c, int32_t b2, int depth)
         load_rec(c->f, open, 1, &ch[best + 1]);
         n++;
     }
+    /* full-precision twin of this node for the packet kernel: the same (up to) four children as 32-byte
+     * records {lo.xyz, hi.x}{hi.y, hi.z, ref, 0} exactly as in the binary tree (leaf refs and boxes unchanged) */
+    float full[32];
+    int full_inner[4], n_full = n;
+    for (int k = 0; k < 4; k++) {
+        float *q = full + 8 * k;
+        full_inner[k] = 0;
+        if (k < n) {
+            q[0] = ch[k].lo[0]; q[1] = ch[k].lo[1]; q[2] = ch[k].lo[2]; q[3] = ch[k].hi[0];
+            q[4] = ch[k].hi[1]; q[5] = ch[k].hi[2]; q[6] = u2f((uint32_t)ch[k].ref); q[7] = 0.0f;
+            full_inner[k] = ch[k].ref >= 0;
+        } else {
+            q[0] = q[1] = q[2] = INFINITY; q[3] = q[4] = q[5] = -INFINITY;
+            q[6] = u2f((uint32_t)SAHBVH_REF_NONE); q[7] = 0.0f;
+        }
+    }
+    int32_t full_slot[4] = {0, 1, 2, 3}; /* slot of child k in `full` (the quantised node drops never-hit leaves) */
     /* resolve leaf refs, drop children that can never hit */
     int m = 0;
     for (int k = 0; k < n; k++) {
@@ -182,9 +207,12 @@ static int32_t emit(ctx_t *c, int32_t b2, int depth)
             if (lr == SAHBVH_REF_NONE) continue;
             ch[k].ref = lr;
         }
+        full_slot[m] = k;
         ch[m++] = ch[k];
     }
     n = m;
+    (void)n_full;
+    (void)full_inner;
 
     uint32_t node[16];
     memset(node, 0, sizeof node);
@@ -207,10 +235,14 @@ static int32_t emit(ctx_t *c, int32_t b2, int depth)
     for (int k = 0; k < 4; k++) node[10 + k] = (uint32_t)SAHBVH_REF_NONE;
     for (int k = 0; k < n; k++) {
         int32_t ref = ch[k].ref;
-        if (ref >= 0) ref = emit(c, ref, depth + 1); /* may reallocate w->nodes */
+        if (ref >= 0) {
+            ref = emit(c, ref, depth + 1); /* may reallocate w->nodes / w->full */
+            full[8 * full_slot[k] + 6] = u2f((uint32_t)ref);
+        }
         node[10 + k] = (uint32_t)ref;
     }
     memcpy(c->w->nodes + (size_t)me * 16, node, 64);
+    memcpy(c->w->full + (size_t)me * 32, full, 128);
     return me;
 }
 
@@ -228,7 +260,8 @@ int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f)
     c.cap_nodes = (int64_t)f->info.n_inner / 2 + 16;
     c.rc = SAHBVH_OK;
     w->nodes = (uint32_t *)aligned_alloc(64, (size_t)c.cap_nodes * 64);
-    if (!w->nodes) return SAHBVH_E_NOMEM;
+    w->full = (float *)aligned_alloc(128, (size_t)c.cap_nodes * 128);
+    if (!w->nodes || !w->full) { wide_bvh_release(w); return SAHBVH_E_NOMEM; }
     emit(&c, 0, 0);
     if (c.rc != SAHBVH_OK) {
         wide_bvh_release(w);
@@ -250,8 +283,10 @@ int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f)
 void wide_bvh_release(wide_bvh *w)
 {
     free(w->nodes);
+    free(w->full);
     free(w->special);
     w->nodes = NULL;
+    w->full = NULL;
     w->special = NULL;
     w->n_wide = w->n_special = 0;
 }
