@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--modes", default="2,1,0")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--kind", default="bounce", choices=["bounce", "bench", "primary"])
+    ap.add_argument("--stride", type=int, default=1, help="generate rays*stride rays and keep every stride-th")
+    ap.add_argument("--tile", default="", help="WxH: take the primary hits in pixel-tile order (e.g. 8x4) instead of row-major")
     args = ap.parse_args()
     import torch
     pkg = g.load_pkg()
@@ -35,13 +37,17 @@ def main():
     torch.cuda.synchronize()
     if args.kind == "bounce":
         hits = buf.cpu().numpy().view(pkg.HIT_DT).reshape(-1)
+        if args.tile:
+            tw, th = [int(v) for v in args.tile.split("x")]
+            idx = np.arange(W * H).reshape(H // th, th, W // tw, tw).transpose(0, 2, 1, 3).reshape(-1)
+            hits = np.ascontiguousarray(hits[idx])
         pkg.srand(2)
         parts, have = [], 0
-        while have < args.rays:
+        while have < args.rays * args.stride:
             r = pkg.bounce_rays(hits)
             parts.append(r)
             have += len(r)
-        rays = np.concatenate(parts)[:args.rays]
+        rays = np.ascontiguousarray(np.concatenate(parts)[:args.rays * args.stride:args.stride])
     elif args.kind == "bench":
         pkg.srand(3)
         rays = pkg.benchmark_rays(args.rays)
