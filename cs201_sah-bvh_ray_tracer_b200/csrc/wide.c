@@ -34,6 +34,7 @@
  * tree's own format, boxes and leaf refs unchanged) with the same numbering: the packet kernel tests one child
  * box per lane, so it gains the halved depth without paying for a decode.
  *
+ * Nodes are numbered breadth first (the upper levels and the up to four children of a node are adjacent).
  * Children are chosen by the usual surface-area greedy collapse: start from the two children of
  * a binary node and repeatedly open the inner child with the largest area until there are 4.
  */
@@ -143,26 +144,32 @@ static int quantise_axis(const rec_t *ch, int n, int a, float *p_out, int *e_out
     return 0;
 }
 
-static int32_t emit(ctx_t *c, int32_t b2, int depth)
+/* make room for node id `need - 1` (both node arrays grow together) */
+static int reserve_nodes(ctx_t *c, int64_t need)
 {
     wide_bvh *w = c->w;
-    if (c->rc != SAHBVH_OK) return SAHBVH_REF_NONE;
-    if (w->n_wide == c->cap_nodes) {
-        int64_t ncap = c->cap_nodes * 2;
-        uint32_t *nn = (uint32_t *)aligned_alloc(64, (size_t)ncap * 64);
-        float *nf = (float *)aligned_alloc(128, (size_t)ncap * 128);
-        if (!nn || !nf) { free(nn); free(nf); c->rc = SAHBVH_E_NOMEM; return SAHBVH_REF_NONE; }
-        memcpy(nn, w->nodes, (size_t)w->n_wide * 64);
-        memcpy(nf, w->full, (size_t)w->n_wide * 128);
-        free(w->nodes);
-        free(w->full);
-        w->nodes = nn;
-        w->full = nf;
-        c->cap_nodes = ncap;
-    }
-    const int32_t me = w->n_wide++;
-    if (depth > c->max_depth) c->max_depth = depth;
+    if (need <= c->cap_nodes) return SAHBVH_OK;
+    int64_t ncap = c->cap_nodes * 2 > need ? c->cap_nodes * 2 : need;
+    uint32_t *nn = (uint32_t *)aligned_alloc(64, (size_t)ncap * 64);
+    float *nf = (float *)aligned_alloc(128, (size_t)ncap * 128);
+    if (!nn || !nf) { free(nn); free(nf); return SAHBVH_E_NOMEM; }
+    const int64_t keep = w->n_wide < c->cap_nodes ? w->n_wide : c->cap_nodes; /* ids beyond the old capacity are not written yet */
+    memcpy(nn, w->nodes, (size_t)keep * 64);
+    memcpy(nf, w->full, (size_t)keep * 128);
+    free(w->nodes);
+    free(w->full);
+    w->nodes = nn;
+    w->full = nf;
+    c->cap_nodes = ncap;
+    return SAHBVH_OK;
+}
 
+/* Node `me` (already numbered) from binary node b2.  Inner children are numbered n_wide, n_wide+1, ... in slot
+ * order and their binary nodes are written to child_b2[] for the caller's queue: the tree comes out in
+ * BREADTH-FIRST order (the device collapse in gpu_builder.cu numbers level by level and must produce the same
+ * bytes; it also puts the upper levels and the four children of a node next to each other). */
+static int emit(ctx_t *c, int32_t b2, int32_t me, int32_t child_b2[4], int *n_child)
+{
     rec_t ch[4];
     int n = 2;
     load_rec(c->f, b2, 0, &ch[0]);
@@ -185,34 +192,34 @@ static int32_t emit(ctx_t *c, int32_t b2, int depth)
     /* full-precision twin of this node for the packet kernel: the same (up to) four children as 32-byte
      * records {lo.xyz, hi.x}{hi.y, hi.z, ref, 0} exactly as in the binary tree (leaf refs and boxes unchanged) */
     float full[32];
-    int full_inner[4], n_full = n;
     for (int k = 0; k < 4; k++) {
         float *q = full + 8 * k;
-        full_inner[k] = 0;
         if (k < n) {
             q[0] = ch[k].lo[0]; q[1] = ch[k].lo[1]; q[2] = ch[k].lo[2]; q[3] = ch[k].hi[0];
             q[4] = ch[k].hi[1]; q[5] = ch[k].hi[2]; q[6] = u2f((uint32_t)ch[k].ref); q[7] = 0.0f;
-            full_inner[k] = ch[k].ref >= 0;
         } else {
             q[0] = q[1] = q[2] = INFINITY; q[3] = q[4] = q[5] = -INFINITY;
             q[6] = u2f((uint32_t)SAHBVH_REF_NONE); q[7] = 0.0f;
         }
     }
-    int32_t full_slot[4] = {0, 1, 2, 3}; /* slot of child k in `full` (the quantised node drops never-hit leaves) */
-    /* resolve leaf refs, drop children that can never hit */
+    /* number the inner children (slot order), resolve leaf refs, drop children that can never hit */
+    *n_child = 0;
     int m = 0;
     for (int k = 0; k < n; k++) {
-        if (ch[k].ref < 0) {
+        if (ch[k].ref >= 0) {
+            const int32_t id = c->w->n_wide++;
+            child_b2[(*n_child)++] = ch[k].ref;
+            ch[k].ref = id;
+            full[8 * k + 6] = u2f((uint32_t)id);
+        } else {
             int32_t lr = leaf_ref(c, &ch[k]);
             if (lr == SAHBVH_REF_NONE) continue;
             ch[k].ref = lr;
         }
-        full_slot[m] = k;
         ch[m++] = ch[k];
     }
+    if (c->rc != SAHBVH_OK) return c->rc;
     n = m;
-    (void)n_full;
-    (void)full_inner;
 
     uint32_t node[16];
     memset(node, 0, sizeof node);
@@ -232,18 +239,12 @@ static int32_t emit(ctx_t *c, int32_t b2, int depth)
             node[7 + a] |= (uint32_t)(k < n ? qhi[k] : 0) << (8 * k);
         }
     }
-    for (int k = 0; k < 4; k++) node[10 + k] = (uint32_t)SAHBVH_REF_NONE;
-    for (int k = 0; k < n; k++) {
-        int32_t ref = ch[k].ref;
-        if (ref >= 0) {
-            ref = emit(c, ref, depth + 1); /* may reallocate w->nodes / w->full */
-            full[8 * full_slot[k] + 6] = u2f((uint32_t)ref);
-        }
-        node[10 + k] = (uint32_t)ref;
-    }
+    for (int k = 0; k < 4; k++) node[10 + k] = k < n ? (uint32_t)ch[k].ref : (uint32_t)SAHBVH_REF_NONE;
+    int rc = reserve_nodes(c, c->w->n_wide);
+    if (rc != SAHBVH_OK) return rc;
     memcpy(c->w->nodes + (size_t)me * 16, node, 64);
     memcpy(c->w->full + (size_t)me * 32, full, 128);
-    return me;
+    return SAHBVH_OK;
 }
 
 int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f)
@@ -262,7 +263,34 @@ int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f)
     w->nodes = (uint32_t *)aligned_alloc(64, (size_t)c.cap_nodes * 64);
     w->full = (float *)aligned_alloc(128, (size_t)c.cap_nodes * 128);
     if (!w->nodes || !w->full) { wide_bvh_release(w); return SAHBVH_E_NOMEM; }
-    emit(&c, 0, 0);
+    {
+        /* breadth-first: queue entry = (binary node, depth); wide id = position in the queue */
+        int64_t qcap = 1024, qn = 1;
+        int32_t *q_b2 = (int32_t *)malloc((size_t)qcap * sizeof(int32_t));
+        int32_t *q_depth = (int32_t *)malloc((size_t)qcap * sizeof(int32_t));
+        if (!q_b2 || !q_depth) { free(q_b2); free(q_depth); wide_bvh_release(w); return SAHBVH_E_NOMEM; }
+        q_b2[0] = 0;
+        q_depth[0] = 0;
+        w->n_wide = 1;
+        for (int64_t i = 0; i < qn && c.rc == SAHBVH_OK; i++) {
+            int32_t kids[4];
+            int nk = 0;
+            if (q_depth[i] > c.max_depth) c.max_depth = q_depth[i];
+            int rc = emit(&c, q_b2[i], (int32_t)i, kids, &nk);
+            if (rc != SAHBVH_OK) { c.rc = rc; break; }
+            if (qn + nk > qcap) {
+                qcap *= 2;
+                int32_t *a = (int32_t *)realloc(q_b2, (size_t)qcap * sizeof(int32_t));
+                int32_t *b = a ? (int32_t *)realloc(q_depth, (size_t)qcap * sizeof(int32_t)) : NULL;
+                if (a) q_b2 = a;
+                if (b) q_depth = b;
+                if (!a || !b) { c.rc = SAHBVH_E_NOMEM; break; }
+            }
+            for (int k = 0; k < nk; k++) { q_b2[qn] = kids[k]; q_depth[qn] = q_depth[i] + 1; qn++; }
+        }
+        free(q_b2);
+        free(q_depth);
+    }
     if (c.rc != SAHBVH_OK) {
         wide_bvh_release(w);
         return c.rc;
