@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "gpu_trace_closest_hit", "gpu_trace_closest_hit_dev", "gpu_trace_primary", "gpu_trace_primary_dev",
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
     "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
-    "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree",
+    "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree", "gpu_bvh_download",
     "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
@@ -249,6 +249,17 @@ class GpuBvh:
             self.close()
         except Exception:
             pass
+
+    def download(self, what: int) -> np.ndarray:
+        """gpu_bvh_download: raw bytes of one device array (0 nodes, 1 spheres4, 2 colours, 3 wide, 4 wide full, 5 special)."""
+        lib.gpu_bvh_download.restype = C.c_int64
+        n = lib.gpu_bvh_download(self._h, C.c_int(what), None, C.c_int64(0))
+        if n < 0:
+            raise SahBvhError(f"gpu_bvh_download failed ({n}): {lib.sahbvh_last_error().decode()}")
+        out = np.empty(n, np.uint8)
+        if n:
+            lib.gpu_bvh_download(self._h, C.c_int(what), _ptr(out), C.c_int64(n))
+        return out
 
     def info(self) -> dict:
         i = BvhInfo()

@@ -65,7 +65,7 @@ struct GbBins {
     uint32_t hi[3][8][3];
 };
 struct GbSmall { int32_t node, start, end, depth; };
-struct GbCounters { int32_t nodes, next_work, small, overflow; };
+struct GbCounters { int32_t nodes, next_work, small, overflow, max_depth, pad[3]; };
 
 #define GB_TRY(expr)                                                                               \
     do {                                                                                           \
@@ -213,7 +213,7 @@ __global__ void k_gb_root_finish(const uint32_t *root_enc, int m, int depth, sah
     n.sphere = -1;
     n.count = 0;
     work[0].node = 0; work[0].start = 0; work[0].end = m; work[0].depth = depth; work[0].mode = 0;
-    ctr->nodes = 1; ctr->next_work = 0; ctr->small = 0; ctr->overflow = 0;
+    ctr->nodes = 1; ctr->next_work = 0; ctr->small = 0; ctr->overflow = 0; ctr->max_depth = 0;
 }
 
 __global__ void k_gb_prepare(GbWork *work, int n_work, const sah_node *__restrict__ nodes, GbBins *bins)
@@ -588,18 +588,20 @@ k_gb_sizes(const sah_node *__restrict__ nodes, int n_nodes, const int32_t *__res
 
 __global__ void __launch_bounds__(GB_THREADS)
 k_gb_emit(const sah_node *__restrict__ nodes, int n_nodes, const int32_t *__restrict__ parent, const int32_t *__restrict__ size,
-          sah_node *out)
+          sah_node *out, GbCounters *ctr)
 {
     const int i = blockIdx.x * GB_THREADS + threadIdx.x;
     if (i >= n_nodes) return;
-    int pre = 0, c = i;
+    int pre = 0, c = i, levels = 0;
     for (;;) {
         const int p = parent[c];
         if (p < 0) break;
         pre += 1;
+        levels++;
         if (nodes[p].right == c) pre += size[nodes[p].left];
         c = p;
     }
+    if (levels > ctr->max_depth) atomicMax(&ctr->max_depth, levels);
     sah_node nd = nodes[i];
     if (nd.sphere < 0) {
         const int ls = size[nd.left];
@@ -618,12 +620,326 @@ k_gb_permute(const Sphere *__restrict__ in, const int32_t *__restrict__ ids, int
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* flatten (flatten.c) and 4-wide collapse (wide.c) on the device: same bytes as the host code    */
+/* ------------------------------------------------------------------------------------------ */
+struct FlStats { int32_t n_leaf, multi, empty, bad_index, max_depth; uint32_t rmax_bits; uint32_t lo[3], hi[3]; int32_t n_special, pad; };
+
+/* generic exclusive scan of uint32 (1024 items per block), three launches */
+__global__ void __launch_bounds__(GB_THREADS) k_scan32_block(const uint32_t *__restrict__ in, int n, uint32_t *out, uint32_t *block_sums)
+{
+    __shared__ uint32_t s_warp[GB_THREADS / 32];
+    const int base = (blockIdx.x * GB_THREADS + threadIdx.x) * GB_SCAN_ITEMS;
+    uint32_t f[GB_SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int j = 0; j < GB_SCAN_ITEMS; j++) {
+        f[j] = base + j < n ? in[base + j] : 0u;
+        sum += f[j];
+    }
+    uint32_t incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = lane < GB_THREADS / 32 ? s_warp[lane] : 0, inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane < GB_THREADS / 32) s_warp[lane] = inc - v;
+        if (lane == GB_THREADS / 32 - 1) block_sums[blockIdx.x] = inc;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < GB_SCAN_ITEMS; j++) {
+        if (base + j < n) out[base + j] = run;
+        run += f[j];
+    }
+}
+__global__ void __launch_bounds__(GB_THREADS) k_scan32_add(uint32_t *out, int n, const uint32_t *__restrict__ block_sums, uint32_t *total)
+{
+    const int i = blockIdx.x * GB_THREADS + threadIdx.x;
+    if (i < n) out[i] += block_sums[i / (GB_THREADS * GB_SCAN_ITEMS)];
+    if (i == 0 && total) {
+        const int last = (n - 1) / (GB_THREADS * GB_SCAN_ITEMS);
+        (void)last;
+    }
+}
+/* out = exclusive scan of in; *total (device) = sum of all; in may alias nothing */
+static void scan32(const uint32_t *d_in, int n, uint32_t *d_out, uint32_t *d_sums)
+{
+    const int sb = (n + GB_THREADS * GB_SCAN_ITEMS - 1) / (GB_THREADS * GB_SCAN_ITEMS);
+    k_scan32_block<<<sb, GB_THREADS>>>(d_in, n, d_out, d_sums);
+    k_gb_scan_sums<<<1, 1024>>>(d_sums, sb);
+    k_scan32_add<<<(n + GB_THREADS - 1) / GB_THREADS, GB_THREADS>>>(d_out, n, d_sums, nullptr);
+}
+
+__global__ void __launch_bounds__(GB_THREADS)
+k_fl_flags(const sah_node *__restrict__ pre, int n_nodes, int n_total, uint32_t *flags, FlStats *st)
+{
+    const int i = blockIdx.x * GB_THREADS + threadIdx.x;
+    if (i >= n_nodes) return;
+    const sah_node nd = pre[i];
+    const bool inner = nd.sphere < 0;
+    flags[i] = inner ? 1u : 0u;
+    if (!inner) {
+        atomicAdd(&st->n_leaf, 1);
+        if (nd.count > 1) atomicAdd(&st->multi, 1);
+        if (nd.count == 0) atomicAdd(&st->empty, 1);
+        if (nd.sphere > n_total) st->bad_index = 1;
+    }
+}
+
+/* flatten.c: inner node -> two 32-byte child records; an empty leaf carries its parent's bounds (Q3) */
+__global__ void __launch_bounds__(GB_THREADS)
+k_fl_nodes(const sah_node *__restrict__ pre, int n_nodes, const uint32_t *__restrict__ inner_id, float *flat)
+{
+    const int i = blockIdx.x * GB_THREADS + threadIdx.x;
+    if (i >= n_nodes) return;
+    const sah_node nd = pre[i];
+    if (nd.sphere >= 0) return;
+    float *w = flat + (size_t)inner_id[i] * 16;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int ci = side ? nd.right : nd.left;
+        const sah_node ch = pre[ci];
+        const bool empty_leaf = ch.sphere >= 0 && ch.count == 0;
+        const float *lo = empty_leaf ? nd.lo : ch.lo, *hi = empty_leaf ? nd.hi : ch.hi;
+        const int32_t ref = ch.sphere >= 0 ? ~ch.sphere : (int32_t)inner_id[ci];
+        float *q = w + 8 * side;
+        q[0] = lo[0]; q[1] = lo[1]; q[2] = lo[2]; q[3] = hi[0];
+        q[4] = hi[1]; q[5] = hi[2]; q[6] = __int_as_float(ref); q[7] = 0.0f;
+    }
+}
+
+/* spheres4 / colours of the WHOLE array (indices are global), max |r| and the bounds of all spheres */
+__global__ void __launch_bounds__(GB_THREADS)
+k_fl_spheres(const Sphere *__restrict__ all, int n_total, float *spheres4, uint32_t *colors, FlStats *st)
+{
+    const int i = blockIdx.x * GB_THREADS + threadIdx.x;
+    if (i > n_total) return;
+    if (i == n_total) { /* the reference's one-past-the-end read: never a hit */
+        const float nan = __int_as_float(0x7fc00000);
+        reinterpret_cast<float4 *>(spheres4)[i] = make_float4(nan, nan, nan, nan);
+        colors[i] = 0;
+        return;
+    }
+    const Sphere s = all[i];
+    reinterpret_cast<float4 *>(spheres4)[i] = make_float4(s.center.x, s.center.y, s.center.z, s.radius);
+    uint32_t c;
+    memcpy(&c, &s.color, 4);
+    colors[i] = c;
+    const float ar = fabsf(s.radius);
+    if (ar == ar) atomicMax(&st->rmax_bits, __float_as_uint(ar));   /* ar >= 0: bit order == value order */
+    const float cc[3] = {s.center.x, s.center.y, s.center.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float lo = cc[a] - ar, hi = cc[a] + ar;
+        if (lo == lo) atomicMin(&st->lo[a], f_enc(lo));
+        if (hi == hi) atomicMax(&st->hi[a], f_enc(hi));
+    }
+}
+
+/* ---- wide collapse, one level per launch pair ---- */
+struct WdRec { float lo[3], hi[3]; int32_t ref; };
+
+__device__ __forceinline__ void wd_load(const float *__restrict__ flat, int32_t node, int child, WdRec &r)
+{
+    const float4 *q = reinterpret_cast<const float4 *>(flat + (size_t)node * 16 + child * 8);
+    const float4 a = q[0], b = q[1];
+    r.lo[0] = a.x; r.lo[1] = a.y; r.lo[2] = a.z; r.hi[0] = a.w; r.hi[1] = b.x; r.hi[2] = b.y;
+    r.ref = __float_as_int(b.z);
+}
+__device__ __forceinline__ float wd_area(const WdRec &r)
+{
+    const float dx = r.hi[0] - r.lo[0], dy = r.hi[1] - r.lo[1], dz = r.hi[2] - r.lo[2];
+    const float a = dx * dy + dy * dz + dz * dx;
+    return a == a ? a : INFINITY;
+}
+/* the greedy collapse of wide.c: up to four children of binary node b2, left-to-right */
+__device__ int wd_collapse(const float *__restrict__ flat, int32_t b2, WdRec ch[4])
+{
+    int n = 2;
+    wd_load(flat, b2, 0, ch[0]);
+    wd_load(flat, b2, 1, ch[1]);
+    while (n < 4) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int k = 0; k < n; k++)
+            if (ch[k].ref >= 0) {
+                const float a = wd_area(ch[k]);
+                if (a > best_area) { best_area = a; best = k; }
+            }
+        if (best < 0) break;
+        const int32_t open = ch[best].ref;
+        for (int k = n; k > best + 1; k--) ch[k] = ch[k - 1];
+        wd_load(flat, open, 0, ch[best]);
+        wd_load(flat, open, 1, ch[best + 1]);
+        n++;
+    }
+    return n;
+}
+/* leaf classification of wide.c: 0 = never hits (dropped), 1 = regular, 2 = special */
+__device__ int wd_leaf_class(const WdRec &r, const float *__restrict__ spheres4, int n_spheres)
+{
+    const int32_t idx = ~r.ref;
+    if (r.ref == SAHBVH_REF_NONE || (uint32_t)idx >= (uint32_t)n_spheres) return 0;
+    const float4 s = reinterpret_cast<const float4 *>(spheres4)[idx];
+    const float lo[3] = {s.x - s.w, s.y - s.w, s.z - s.w}, hi[3] = {s.x + s.w, s.y + s.w, s.z + s.w};
+    bool same = true;
+    for (int a = 0; a < 3; a++)
+        same = same && __float_as_uint(lo[a]) == __float_as_uint(r.lo[a]) && __float_as_uint(hi[a]) == __float_as_uint(r.hi[a]);
+    return same ? 1 : 2;
+}
+
+__global__ void __launch_bounds__(128)
+k_wd_count(const float *__restrict__ flat, const float *__restrict__ spheres4, int n_spheres,
+           const int32_t *__restrict__ frontier, int n_front, uint32_t *cnt_inner, uint32_t *cnt_special)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_front) return;
+    WdRec ch[4];
+    const int n = wd_collapse(flat, frontier[i], ch);
+    uint32_t ni = 0, ns = 0;
+    for (int k = 0; k < n; k++) {
+        if (ch[k].ref >= 0) ni++;
+        else if (wd_leaf_class(ch[k], spheres4, n_spheres) == 2) ns++;
+    }
+    cnt_inner[i] = ni;
+    cnt_special[i] = ns;
+}
+
+/* quantise_axis of wide.c, in double (the host's long-double containment check is re-evaluated in double:
+ * the margins are 2^20 times wider than double rounding) */
+__device__ int wd_quantise_axis(const WdRec *ch, int n, int a, float &p_out, int &e_out, uint8_t qlo[4], uint8_t qhi[4])
+{
+    double mn = INFINITY, mx = -INFINITY, maxabs = 0.0;
+    for (int k = 0; k < n; k++) {
+        const double lo = ch[k].lo[a], hi = ch[k].hi[a];
+        if (!isfinite(lo) || !isfinite(hi) || lo > hi) return -1;
+        if (lo < mn) mn = lo;
+        if (hi > mx) mx = hi;
+        if (fabs(lo) > maxabs) maxabs = fabs(lo);
+        if (fabs(hi) > maxabs) maxabs = fabs(hi);
+    }
+    if (n == 0) return -1;
+    const double ext = mx - mn;
+    int e = -60;
+    if (ext > 0.0) {
+        int ee;
+        frexp(ext / 253.0, &ee);
+        if (ee > e) e = ee;
+    }
+    if (maxabs > 0.0) {
+        int ea;
+        frexp(maxabs, &ea);
+        if (ea - 24 + 3 > e) e = ea - 24 + 3;
+    }
+    if (e > 27) return -1;
+    const double s = ldexp(1.0, e);
+    float p = __double2float_rn(mn - 1024.5 * s);
+    while ((double)p > mn - 1024.25 * s) p = nextafterf(p, -INFINITY);
+    if (!isfinite(p)) return -1;
+    for (int k = 0; k < n; k++) {
+        const double l = floor(((double)ch[k].lo[a] - (double)p) / s - 1024.0 - 1.0 / 256.0);
+        const double h = ceil(((double)ch[k].hi[a] - (double)p) / s - 1024.0 + 1.0 / 256.0);
+        if (l < 0.0 || h > 255.0) return -1;
+        const double dl = (double)p + (1024.0 + l) * s, dh = (double)p + (1024.0 + h) * s, m = s / 512.0;
+        if (!(dl <= (double)ch[k].lo[a] - m) || !(dh >= (double)ch[k].hi[a] + m)) return -1;
+        qlo[k] = (uint8_t)l;
+        qhi[k] = (uint8_t)h;
+    }
+    p_out = p;
+    e_out = e;
+    return 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_wd_emit(const float *__restrict__ flat, const float *__restrict__ spheres4, int n_spheres,
+          const int32_t *__restrict__ frontier, int n_front, int first_id, const uint32_t *__restrict__ off_inner,
+          const uint32_t *__restrict__ off_special, int next_first_id, int special_base,
+          uint32_t *wide, float *full, float *special, int32_t *next_frontier)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_front) return;
+    const int32_t me = first_id + i;
+    WdRec ch[4];
+    int n = wd_collapse(flat, frontier[i], ch);
+    float fl[32];
+    for (int k = 0; k < 4; k++) {
+        float *q = fl + 8 * k;
+        if (k < n) {
+            q[0] = ch[k].lo[0]; q[1] = ch[k].lo[1]; q[2] = ch[k].lo[2]; q[3] = ch[k].hi[0];
+            q[4] = ch[k].hi[1]; q[5] = ch[k].hi[2]; q[6] = __int_as_float(ch[k].ref); q[7] = 0.0f;
+        } else {
+            q[0] = q[1] = q[2] = INFINITY; q[3] = q[4] = q[5] = -INFINITY;
+            q[6] = __int_as_float(SAHBVH_REF_NONE); q[7] = 0.0f;
+        }
+    }
+    int ni = 0, ns = 0, m = 0;
+    for (int k = 0; k < n; k++) {
+        if (ch[k].ref >= 0) {
+            const int32_t id = next_first_id + (int32_t)off_inner[i] + ni;
+            next_frontier[off_inner[i] + ni] = ch[k].ref;
+            ni++;
+            ch[k].ref = id;
+            fl[8 * k + 6] = __int_as_float(id);
+        } else {
+            const int cls = wd_leaf_class(ch[k], spheres4, n_spheres);
+            if (cls == 0) continue;
+            if (cls == 2) {
+                const int32_t sk = special_base + (int32_t)off_special[i] + ns;
+                ns++;
+                float *q = special + (size_t)sk * 8;
+                q[0] = ch[k].lo[0]; q[1] = ch[k].lo[1]; q[2] = ch[k].lo[2]; q[3] = ch[k].hi[0];
+                q[4] = ch[k].hi[1]; q[5] = ch[k].hi[2]; q[6] = __int_as_float(~ch[k].ref); q[7] = 0.0f;
+                ch[k].ref = ~(int32_t)(SAHBVH_WIDE_SPECIAL | (uint32_t)sk);
+            }
+        }
+        ch[m++] = ch[k];
+    }
+    n = m;
+    uint32_t node[16];
+    for (int k = 0; k < 16; k++) node[k] = 0;
+    const int s_word[3] = {3, 14, 15};
+    for (int a = 0; a < 3; a++) {
+        float p = __int_as_float(0x7fc00000);
+        int e = 0;
+        uint8_t qlo[4] = {255, 255, 255, 255}, qhi[4] = {0, 0, 0, 0};
+        if (wd_quantise_axis(ch, n, a, p, e, qlo, qhi) != 0) {
+            p = __int_as_float(0x7fc00000);
+            e = 0;
+        }
+        node[a] = __float_as_uint(p);
+        node[s_word[a]] = __float_as_uint(ldexpf(1.0f, e));
+        for (int k = 0; k < 4; k++) {
+            node[4 + a] |= (uint32_t)(k < n ? qlo[k] : 255) << (8 * k);
+            node[7 + a] |= (uint32_t)(k < n ? qhi[k] : 0) << (8 * k);
+        }
+    }
+    for (int k = 0; k < 4; k++) node[10 + k] = k < n ? (uint32_t)ch[k].ref : (uint32_t)SAHBVH_REF_NONE;
+    uint4 *wo = reinterpret_cast<uint4 *>(wide + (size_t)me * 16);
+    for (int k = 0; k < 4; k++) wo[k] = make_uint4(node[4 * k], node[4 * k + 1], node[4 * k + 2], node[4 * k + 3]);
+    float4 *fo = reinterpret_cast<float4 *>(full + (size_t)me * 32);
+    for (int k = 0; k < 8; k++) fo[k] = make_float4(fl[4 * k], fl[4 * k + 1], fl[4 * k + 2], fl[4 * k + 3]);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* host driver                                                                                  */
 /* ------------------------------------------------------------------------------------------ */
-extern "C" int sah_build_gpu(sah_tree *t, Sphere *spheres, int start, int end, int depth, int device)
+static int flatten_and_collapse(const sah_node *d_pre, int n_nodes, int tree_depth, const Sphere *d_all, int n_total,
+                                gpu_bvh_parts *parts, bool timing);
+
+/* t != NULL: tree to the host (preorder sah_tree).  parts != NULL: tree stays on the device and is flattened and
+ * collapsed there; only the permuted spheres go back.  Returns 1 when the host path has to take over. */
+static int gb_build(sah_tree *t, Sphere *spheres, int n_total, int start, int end, int depth, int device, gpu_bvh_parts *parts)
 {
     const int m = end - start;
-    if (m <= GB_SMALL * 4 || depth >= GB_LEAF_DEPTH) return sah_build(t, spheres, start, end, depth); /* nothing to parallelise */
+    if (m <= GB_SMALL * 4 || depth >= GB_LEAF_DEPTH) return 1; /* nothing to parallelise */
     int rc = SAHBVH_OK;
     int prev_dev = -1;
     cudaGetDevice(&prev_dev);
@@ -736,11 +1052,28 @@ extern "C" int sah_build_gpu(sah_tree *t, Sphere *spheres, int start, int end, i
         const int nb = (h_ctr.nodes + GB_THREADS - 1) / GB_THREADS;
         GB_TRY(cudaMemset(d_visit, 0, (size_t)h_ctr.nodes * sizeof(int32_t)));
         k_gb_sizes<<<nb, GB_THREADS>>>(d_nodes, h_ctr.nodes, d_parent, d_visit, d_size);
-        k_gb_emit<<<nb, GB_THREADS>>>(d_nodes, h_ctr.nodes, d_parent, d_size, d_pre);
+        k_gb_emit<<<nb, GB_THREADS>>>(d_nodes, h_ctr.nodes, d_parent, d_size, d_pre, d_ctr);
         k_gb_permute<<<blocks, GB_THREADS>>>(d_in, d_ids[cur], m, d_out_sph);
         GB_TRY(cudaGetLastError());
     }
     lap("preorder renumbering + sphere permutation");
+    if (parts) {
+        GB_TRY(cudaMemcpy(&h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost));
+        GB_TRY(cudaMemcpy(spheres + start, d_out_sph, (size_t)m * sizeof(Sphere), cudaMemcpyDeviceToHost));
+        lap("D2H permuted spheres");
+        Sphere *d_all = d_out_sph;
+        Sphere *d_all_owned = nullptr;
+        if (start != 0 || end != n_total) { /* indices are global: the kernels need the whole array */
+            GB_TRY(cudaMalloc((void **)&d_all_owned, (size_t)n_total * sizeof(Sphere)));
+            cudaError_t e = cudaMemcpy(d_all_owned, spheres, (size_t)n_total * sizeof(Sphere), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d_all_owned); sahbvh_set_error("gpu builder: %s", cudaGetErrorString(e)); rc = SAHBVH_E_CUDA; goto done; }
+            d_all = d_all_owned;
+        }
+        rc = flatten_and_collapse(d_pre, h_ctr.nodes, h_ctr.max_depth, d_all, n_total, parts, timing);
+        cudaFree(d_all_owned);
+        lap("flatten + wide collapse (device)");
+        goto done;
+    }
     if (t->cap < h_ctr.nodes) {
         sah_node *nn = (sah_node *)realloc(t->nodes, (size_t)h_ctr.nodes * sizeof(sah_node));
         if (!nn) { rc = SAHBVH_E_NOMEM; goto done; }
@@ -754,6 +1087,163 @@ extern "C" int sah_build_gpu(sah_tree *t, Sphere *spheres, int start, int end, i
 done:
     cudaFree(pool);
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    return rc;
+}
+
+extern "C" int sah_build_gpu(sah_tree *t, Sphere *spheres, int start, int end, int depth, int device)
+{
+    int rc = gb_build(t, spheres, end, start, end, depth, device, nullptr);
     if (rc == 1) return sah_build(t, spheres, start, end, depth);
+    return rc;
+}
+
+extern "C" void gpu_bvh_parts_release(gpu_bvh_parts *p)
+{
+    if (!p) return;
+    cudaFree(p->d_nodes); cudaFree(p->d_spheres4); cudaFree(p->d_colors);
+    cudaFree(p->d_wide); cudaFree(p->d_wide_full); cudaFree(p->d_special);
+    memset(p, 0, sizeof *p);
+}
+
+/* build + flatten + collapse, everything on the device; 1 = caller must use the host path instead */
+extern "C" int gpu_build_parts(Sphere *spheres, int n_total, int start, int end, int depth, int device, gpu_bvh_parts *parts)
+{
+    memset(parts, 0, sizeof *parts);
+    int rc = gb_build(nullptr, spheres, n_total, start, end, depth, device, parts);
+    if (rc != SAHBVH_OK) gpu_bvh_parts_release(parts);
+    return rc;
+}
+
+#define FC_TRY(expr)                                                                               \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            sahbvh_set_error("gpu flatten: %s failed: %s", #expr, cudaGetErrorString(_e));        \
+            rc = SAHBVH_E_CUDA;                                                                    \
+            goto out;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+static int flatten_and_collapse(const sah_node *d_pre, int n_nodes, int tree_depth, const Sphere *d_all, int n_total,
+                                gpu_bvh_parts *parts, bool timing)
+{
+    int rc = SAHBVH_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gpu flatten] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
+    uint32_t *d_flags = nullptr, *d_inner_id = nullptr, *d_sums = nullptr;
+    uint32_t *d_cnt_i = nullptr, *d_cnt_s = nullptr, *d_off_i = nullptr, *d_off_s = nullptr, *d_wide_tmp = nullptr;
+    int32_t *d_front[2] = {nullptr, nullptr};
+    float *d_full_tmp = nullptr, *d_special_tmp = nullptr;
+    FlStats *d_st = nullptr;
+    FlStats h_st;
+    uint32_t last[2];
+    int n_inner = 0, n_front = 1, first_id = 0, special_base = 0, levels = 0, cur = 0;
+    const int nb = (n_nodes + GB_THREADS - 1) / GB_THREADS;
+    const int sums_cap = (n_nodes + GB_THREADS * GB_SCAN_ITEMS - 1) / (GB_THREADS * GB_SCAN_ITEMS) + 1;
+
+    memset(&h_st, 0, sizeof h_st);
+    for (int a = 0; a < 3; a++) { h_st.lo[a] = ENC_POS_INF; h_st.hi[a] = ENC_NEG_INF; }
+    FC_TRY(cudaMalloc((void **)&d_st, sizeof(FlStats)));
+    FC_TRY(cudaMemcpy(d_st, &h_st, sizeof h_st, cudaMemcpyHostToDevice));
+    FC_TRY(cudaMalloc((void **)&d_flags, (size_t)n_nodes * 4));
+    FC_TRY(cudaMalloc((void **)&d_inner_id, (size_t)n_nodes * 4));
+    FC_TRY(cudaMalloc((void **)&d_sums, (size_t)sums_cap * 4));
+    k_fl_flags<<<nb, GB_THREADS>>>(d_pre, n_nodes, n_total, d_flags, d_st);
+    scan32(d_flags, n_nodes, d_inner_id, d_sums);
+    FC_TRY(cudaGetLastError());
+    FC_TRY(cudaMemcpy(&last[0], d_inner_id + (n_nodes - 1), 4, cudaMemcpyDeviceToHost));
+    FC_TRY(cudaMemcpy(&last[1], d_flags + (n_nodes - 1), 4, cudaMemcpyDeviceToHost));
+    n_inner = (int)(last[0] + last[1]);
+    FC_TRY(cudaMemcpy(&h_st, d_st, sizeof h_st, cudaMemcpyDeviceToHost));
+    lap("flags + scan");
+    if (h_st.bad_index || tree_depth + 2 > SAHBVH_STACK_MAX || n_inner <= 0 || 3 * (tree_depth + 1) + 4 > SAHBVH_WIDE_STACK_MAX) {
+        rc = 1; /* the host flattener reports these cases */
+        goto out;
+    }
+    /* ---- flatten ---- */
+    FC_TRY(cudaMalloc((void **)&parts->d_nodes, (size_t)n_inner * 64));
+    FC_TRY(cudaMalloc((void **)&parts->d_spheres4, ((size_t)n_total + 1) * 16));
+    FC_TRY(cudaMalloc((void **)&parts->d_colors, ((size_t)n_total + 1) * 4));
+    k_fl_nodes<<<nb, GB_THREADS>>>(d_pre, n_nodes, d_inner_id, parts->d_nodes);
+    k_fl_spheres<<<(n_total + 1 + GB_THREADS - 1) / GB_THREADS, GB_THREADS>>>(d_all, n_total, parts->d_spheres4, parts->d_colors, d_st);
+    FC_TRY(cudaGetLastError());
+    lap("flatten (alloc + kernels)");
+    /* ---- wide collapse, level by level (breadth-first numbering, like wide.c) ---- */
+    FC_TRY(cudaMalloc((void **)&d_front[0], (size_t)n_inner * 4));
+    FC_TRY(cudaMalloc((void **)&d_front[1], (size_t)n_inner * 4));
+    FC_TRY(cudaMalloc((void **)&d_cnt_i, (size_t)n_inner * 4));
+    FC_TRY(cudaMalloc((void **)&d_cnt_s, (size_t)n_inner * 4));
+    FC_TRY(cudaMalloc((void **)&d_off_i, (size_t)n_inner * 4));
+    FC_TRY(cudaMalloc((void **)&d_off_s, (size_t)n_inner * 4));
+    FC_TRY(cudaMalloc((void **)&d_wide_tmp, (size_t)n_inner * 64));
+    FC_TRY(cudaMalloc((void **)&d_full_tmp, (size_t)n_inner * 128));
+    FC_TRY(cudaMalloc((void **)&d_special_tmp, ((size_t)h_st.n_leaf + 1) * 32));
+    FC_TRY(cudaMemset(d_front[0], 0, 4));
+    lap("collapse: temp alloc");
+    while (n_front > 0) {
+        const int fb = (n_front + 127) / 128;
+        uint32_t tot[4];
+        k_wd_count<<<fb, 128>>>(parts->d_nodes, parts->d_spheres4, n_total, d_front[cur], n_front, d_cnt_i, d_cnt_s);
+        scan32(d_cnt_i, n_front, d_off_i, d_sums);
+        scan32(d_cnt_s, n_front, d_off_s, d_sums);
+        FC_TRY(cudaGetLastError());
+        FC_TRY(cudaMemcpy(&tot[0], d_off_i + (n_front - 1), 4, cudaMemcpyDeviceToHost));
+        FC_TRY(cudaMemcpy(&tot[1], d_cnt_i + (n_front - 1), 4, cudaMemcpyDeviceToHost));
+        FC_TRY(cudaMemcpy(&tot[2], d_off_s + (n_front - 1), 4, cudaMemcpyDeviceToHost));
+        FC_TRY(cudaMemcpy(&tot[3], d_cnt_s + (n_front - 1), 4, cudaMemcpyDeviceToHost));
+        const int next_front = (int)(tot[0] + tot[1]), n_spec = (int)(tot[2] + tot[3]);
+        if (first_id + n_front + next_front > n_inner || special_base + n_spec > h_st.n_leaf + 1) { rc = 1; goto out; }
+        k_wd_emit<<<fb, 128>>>(parts->d_nodes, parts->d_spheres4, n_total, d_front[cur], n_front, first_id, d_off_i, d_off_s,
+                               first_id + n_front, special_base, d_wide_tmp, d_full_tmp, d_special_tmp, d_front[cur ^ 1]);
+        FC_TRY(cudaGetLastError());
+        first_id += n_front;
+        special_base += n_spec;
+        n_front = next_front;
+        cur ^= 1;
+        levels++;
+    }
+    lap("collapse: levels");
+    parts->n_wide = first_id;
+    parts->n_special = special_base;
+    FC_TRY(cudaMalloc((void **)&parts->d_wide, (size_t)first_id * 64));
+    FC_TRY(cudaMalloc((void **)&parts->d_wide_full, (size_t)first_id * 128));
+    FC_TRY(cudaMalloc((void **)&parts->d_special, (size_t)(special_base > 0 ? special_base : 1) * 32));
+    FC_TRY(cudaMemcpy(parts->d_wide, d_wide_tmp, (size_t)first_id * 64, cudaMemcpyDeviceToDevice));
+    FC_TRY(cudaMemcpy(parts->d_wide_full, d_full_tmp, (size_t)first_id * 128, cudaMemcpyDeviceToDevice));
+    if (special_base > 0) FC_TRY(cudaMemcpy(parts->d_special, d_special_tmp, (size_t)special_base * 32, cudaMemcpyDeviceToDevice));
+    else FC_TRY(cudaMemset(parts->d_special, 0, 32));
+    FC_TRY(cudaMemcpy(&h_st, d_st, sizeof h_st, cudaMemcpyDeviceToHost));
+    {
+        gpu_bvh_info &info = parts->info;
+        memset(&info, 0, sizeof info);
+        info.n_spheres = n_total;
+        info.n_inner = n_inner;
+        info.n_leaf_refs = h_st.n_leaf;
+        info.max_depth = tree_depth;
+        info.multi_leaves = h_st.multi;
+        info.empty_leaves = h_st.empty;
+        info.n_wide = first_id;
+        uint32_t rb = h_st.rmax_bits;
+        memcpy(&info.max_radius, &rb, 4);
+        for (int a = 0; a < 3; a++) {
+            const uint32_t lo = h_st.lo[a], hi = h_st.hi[a];
+            const uint32_t lob = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo, hib = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
+            memcpy(&info.scene_lo[a], &lob, 4);
+            memcpy(&info.scene_hi[a], &hib, 4);
+        }
+        info.device_bytes = (int64_t)n_inner * 64 + ((int64_t)n_total + 1) * 20 + (int64_t)first_id * 192 + (int64_t)(special_base > 0 ? special_base : 1) * 32;
+    }
+    lap("collapse: right-sized copies");
+    (void)levels;
+out:
+    cudaFree(d_st); cudaFree(d_flags); cudaFree(d_inner_id); cudaFree(d_sums);
+    cudaFree(d_front[0]); cudaFree(d_front[1]); cudaFree(d_cnt_i); cudaFree(d_cnt_s); cudaFree(d_off_i); cudaFree(d_off_s);
+    cudaFree(d_wide_tmp); cudaFree(d_full_tmp); cudaFree(d_special_tmp);
     return rc;
 }

@@ -74,6 +74,20 @@ void flat_bvh_release(flat_bvh *f);
  * tiny ranges and when a degenerate input outgrows its node pool) */
 int sah_build_gpu(sah_tree *t, Sphere *spheres, int start, int end, int depth, int device);
 
+/* everything gpu_bvh needs, built and left on the device by gpu_builder.cu (device pointers, owned by the caller) */
+typedef struct gpu_bvh_parts {
+    float *d_nodes;       /* binary flattened nodes, 64 B each */
+    float *d_spheres4;    /* (n_spheres + 1) float4 */
+    uint32_t *d_colors;   /* (n_spheres + 1) RGBA8 */
+    uint32_t *d_wide;     /* 4-wide quantised nodes, 64 B each */
+    float *d_wide_full;   /* their full-precision twins, 128 B each */
+    float *d_special;     /* special-leaf records, 32 B each */
+    int32_t n_wide, n_special;
+    gpu_bvh_info info;
+} gpu_bvh_parts;
+int gpu_build_parts(Sphere *spheres, int n_total, int start, int end, int depth, int device, gpu_bvh_parts *parts);
+void gpu_bvh_parts_release(gpu_bvh_parts *parts);
+
 /* wide.c */
 int wide_bvh_from_flat(wide_bvh *w, const flat_bvh *f);
 void wide_bvh_release(wide_bvh *w);

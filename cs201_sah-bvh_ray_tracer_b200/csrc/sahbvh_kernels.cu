@@ -812,6 +812,69 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
     return SAHBVH_OK;
 }
 
+/* handle around arrays the device builder left on the GPU (takes ownership of the pointers) */
+static int gpu_bvh_from_parts(gpu_bvh_parts *p, int device, gpu_bvh **out)
+{
+    *out = nullptr;
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        sahbvh_set_error("cudaSetDevice(%d) failed", device);
+        return SAHBVH_E_CUDA;
+    }
+    gpu_bvh *b = (gpu_bvh *)calloc(1, sizeof(gpu_bvh));
+    if (!b) return SAHBVH_E_NOMEM;
+    b->device = device;
+    b->info = p->info;
+    b->info.device = device;
+    b->d_nodes = p->d_nodes; b->d_spheres4 = p->d_spheres4; b->d_colors = p->d_colors;
+    b->d_wide = p->d_wide; b->d_wide_full = p->d_wide_full; b->d_special = p->d_special;
+    b->n_wide = p->n_wide; b->n_special = p->n_special;
+    memset(p, 0, sizeof *p);
+    cudaError_t err = cudaSuccess;
+    do {
+        if ((err = cudaMalloc(&b->d_counters, 72 * sizeof(unsigned long long))) != cudaSuccess) break;
+        if ((err = cudaStreamCreateWithFlags(&b->streams[0], cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((err = cudaStreamCreateWithFlags(&b->streams[1], cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((err = cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) break;
+    } while (0);
+    if (err != cudaSuccess) {
+        sahbvh_set_error("gpu_bvh set-up failed: %s", cudaGetErrorString(err));
+        gpu_bvh_free(b);
+        return SAHBVH_E_CUDA;
+    }
+    *out = b;
+    return SAHBVH_OK;
+}
+
+/* Diagnostic download of the handle's device arrays (tests compare the device-built arrays with the host-built
+ * ones byte for byte).  what: 0 binary nodes, 1 spheres4, 2 colours, 3 wide nodes, 4 wide full-precision twins,
+ * 5 special-leaf records.  Returns the array's size in bytes; copies min(size, cap) bytes when out != NULL. */
+extern "C" int64_t gpu_bvh_download(const gpu_bvh *b, int what, void *out, int64_t cap)
+{
+    if (!b) return SAHBVH_E_ARG;
+    const void *src = nullptr;
+    int64_t bytes = 0;
+    switch (what) {
+    case 0: src = b->d_nodes; bytes = (int64_t)b->info.n_inner * 64; break;
+    case 1: src = b->d_spheres4; bytes = ((int64_t)b->info.n_spheres + 1) * 16; break;
+    case 2: src = b->d_colors; bytes = ((int64_t)b->info.n_spheres + 1) * 4; break;
+    case 3: src = b->d_wide; bytes = (int64_t)b->n_wide * 64; break;
+    case 4: src = b->d_wide_full; bytes = (int64_t)b->n_wide * 128; break;
+    case 5: src = b->d_special; bytes = (int64_t)b->n_special * 32; break;
+    default: sahbvh_set_error("gpu_bvh_download: unknown array %d", what); return SAHBVH_E_ARG;
+    }
+    if (out && bytes > 0) {
+        DeviceGuard guard(b->device);
+        const int64_t n = bytes < cap ? bytes : cap;
+        if (n > 0 && cudaMemcpy(out, src, (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            sahbvh_set_error("gpu_bvh_download: copy failed");
+            return SAHBVH_E_CUDA;
+        }
+    }
+    return bytes;
+}
+
 extern "C" int gpu_bvh_upload(const Sphere *permuted, int n, const BVHNode *root, int device, gpu_bvh **out)
 {
     if (!out) {
@@ -839,19 +902,26 @@ extern "C" int gpu_bvh_build(Sphere *spheres, int n_total, int start, int end, i
         return SAHBVH_E_ARG;
     }
     *out = nullptr;
+    if (g_build_mode.load() == SAHBVH_BUILD_DEVICE && end - start >= 4096) {
+        /* build, flatten and collapse on the device: only the permuted spheres come back */
+        if (sahbvh_device_count() == 0) {
+            sahbvh_set_error("no usable CUDA device; this library has no CPU traversal path");
+            return SAHBVH_E_CUDA;
+        }
+        gpu_bvh_parts parts;
+        int prc = gpu_build_parts(spheres, n_total, start, end, depth, device, &parts);
+        if (prc == SAHBVH_OK) {
+            prc = gpu_bvh_from_parts(&parts, device, out);
+            if (prc != SAHBVH_OK) gpu_bvh_parts_release(&parts);
+            return prc;
+        }
+        if (prc != 1) return prc;
+        /* 1: input the device path does not take (degenerate tree, depth limits): the host path below decides */
+    }
     sah_tree t;
     int rc = sah_tree_init(&t, 2 * (int64_t)(end - start + 1) + 16);
     if (rc != SAHBVH_OK) return rc;
-    if (g_build_mode.load() == SAHBVH_BUILD_DEVICE && end - start >= 4096) {
-        if (sahbvh_device_count() == 0) {
-            sahbvh_set_error("no usable CUDA device; this library has no CPU traversal path");
-            sah_tree_free(&t);
-            return SAHBVH_E_CUDA;
-        }
-        rc = sah_build_gpu(&t, spheres, start, end, depth, device);
-    } else {
-        rc = sah_build(&t, spheres, start, end, depth);
-    }
+    rc = sah_build(&t, spheres, start, end, depth);
     flat_bvh f;
     memset(&f, 0, sizeof f);
     if (rc == SAHBVH_OK) rc = flat_bvh_from_tree(&f, &t, spheres, n_total);

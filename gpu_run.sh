@@ -1,3 +1,5 @@
 #!/bin/bash
-python tools/bounce_bench.py --modes 2 --steps 5 2>&1 | grep "mode 2"
-python tools/primary_bench.py 2>&1 | grep "mode 1"
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+SAHBVH_BUILD_TIMING=1 python tools/build_bench.py 100000 10000000 > gpurun_out/build_timing.log 2>&1; grep -E "^\{" gpurun_out/build_timing.log; grep "gpu builder" gpurun_out/build_timing.log | tail -9

@@ -98,6 +98,10 @@ int64_t sahbvh_build_tree(Sphere *spheres, int start, int end, int depth, int mo
                           sahbvh_tree_node *out, int64_t cap);
 
 void gpu_bvh_free(gpu_bvh *bvh);
+/* Diagnostic copy of the handle's device arrays to the host.  what: 0 binary 64-byte nodes, 1 float4 spheres,
+ * 2 RGBA8 colours, 3 4-wide quantised nodes (64 B), 4 their full-precision twins (128 B), 5 special-leaf records
+ * (32 B).  Returns the array's size in bytes (negative = error) and copies min(size, cap) bytes when out != NULL. */
+int64_t gpu_bvh_download(const gpu_bvh *bvh, int what, void *out, int64_t cap);
 int gpu_bvh_get_info(const gpu_bvh *bvh, gpu_bvh_info *info);
 
 /* Closest hit for a ray buffer.  HOST buffers: H2D copy of rays, kernel, D2H copy of hits,

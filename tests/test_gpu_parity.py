@@ -623,3 +623,38 @@ def test_hits_rebuilt_from_primitive_ids(gpu, oracle, scene100k):
         assert same(hits["prim"], d_prims.cpu().numpy())
         assert_hits_equal(d_back.cpu().numpy().view(HIT_DT).reshape(-1), hits, f"rebuilt from ids {w}x{h}")
         assert (hits["prim"] >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("kind,n,build", [
+    ("bench", 5000, (0, 4999, 20)), ("bench", 200000, (0, 199999, 20)), ("bench", 100000, (0, 100000, 0)),
+    ("random", 5000, (0, 5000, 0)), ("random", 60000, (0, 60000, 0)), ("random", 20000, (1000, 19000, 3)),
+    ("bench", 1000000, (0, 1000000, 0)),
+])
+def test_device_flatten_and_collapse_match_host(gpu, oracle, kind, n, build):
+    """gpu_bvh_build in device mode (build + flatten + 4-wide collapse on the GPU) leaves the same bytes in every
+    device array as the host pipeline (sah_builder.c + flatten.c + wide.c), and the same sphere permutation."""
+    oracle.srand(17 + n % 89)
+    so = oracle.scene_benchmark(n) if kind == "bench" else oracle.scene_random(n)
+    arrays, infos, perms = [], [], []
+    try:
+        for mode in (gpu.BUILD_HOST, gpu.BUILD_DEVICE):
+            gpu.set_build_mode(mode)
+            s = so.copy()
+            bvh = gpu.GpuBvh.build(s, n, *build)
+            arrays.append([bvh.download(k) for k in range(6)])
+            info = bvh.info()
+            info.pop("device_bytes")
+            infos.append(info)
+            perms.append(s)
+            bvh.close()
+    finally:
+        gpu.set_build_mode(gpu.BUILD_DEVICE)
+    assert same(perms[0], perms[1])
+    assert infos[0] == infos[1], (infos[0], infos[1])
+    names = ("binary nodes", "spheres4", "colours", "wide nodes", "wide full", "special leaves")
+    for k, name in enumerate(names):
+        a, b = arrays[0][k], arrays[1][k]
+        assert len(a) == len(b), name
+        if not same(a, b):
+            bad = np.nonzero(a != b)[0]
+            raise AssertionError(f"{name}: {len(bad)} bytes differ, first at byte {bad[0]}")
