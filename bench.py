@@ -336,6 +336,30 @@ def run_b200(args):
     launches = pkg.kernel_launches() - launches0
     clk = clocks.stop()
     assembled_ok = None
+    render_multi = None
+    if dist_on:
+        # config-5 style frame assembly of the full path loop: every rank renders its band (trace_ray, MAX_DEPTH 5,
+        # 1 spp, counter-based draws) and the RGBA8 framebuffer (4 B/pixel) is all-gathered; same timing method
+        rgba = torch.empty((world, n_local), dtype=torch.int32, device="cuda")
+
+        def render_step():
+            bvh.render_frame_dev(cam, W, H, y0, y1, 5, 1, rgba[rank].data_ptr(), stream)
+            dist.all_gather_into_tensor(rgba.view(world * n_local), rgba[rank])
+
+        for _ in range(2):
+            render_step()
+        fence()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r_steps = max(3, min(args.steps, 5))
+        r0.record()
+        for _ in range(r_steps):
+            render_step()
+        r1.record()
+        fence()
+        tr = torch.tensor([r0.elapsed_time(r1) / r_steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        render_multi = {"workload": f"path loop (renderer.c:21-76), {W}x{H}, MAX_DEPTH 5, 1 spp, row bands + NCCL all_gather of the RGBA8 frame",
+                        "ms_per_frame": float(tr.item()), "value": total_rays / (float(tr.item()) * 1e-3) / 1e9, "unit": "Gpaths/s"}
     if dist_on:
         # untimed check of the assembled frame: the records rebuilt from the gathered ids of the NEXT rank's band must
         # equal what that rank traced (exchanged here through one more all_gather of a 64 K-pixel sample)
@@ -467,6 +491,8 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "sweep": sweep,
     }
+    if render_multi is not None:
+        line["render_path"] = render_multi
     if assembled_ok is not None:
         line["config"]["assembled_frame_check"] = ("records rebuilt from the gathered ids == the owning rank's traced records "
                                                    "(bit-exact, 64 K-pixel sample per rank): " + ("pass" if assembled_ok else "FAIL"))

@@ -1,5 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-SAHBVH_BUILD_TIMING=1 python tools/build_bench.py 100000 10000000 > gpurun_out/build_timing.log 2>&1; grep -E "^\{" gpurun_out/build_timing.log; grep "gpu builder" gpurun_out/build_timing.log | tail -9
+N=${1:-2}
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "exit $?"
+tail -3 gpurun_out/bench_n$N.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_n$N.json').read().strip().splitlines()[-1])
+print('N',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'], d.get('render_path'), d['config'].get('assembled_frame_check'), d['clocks'])
+PY
