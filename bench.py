@@ -427,11 +427,19 @@ def run_b200(args):
     k_s = k_ms * 1e-3
     compulsory_bytes = 32 * n_local + info["n_wide"] * 128 + (info["n_spheres"] + 1) * 16
     touched_bytes = 128 * stats["inner_visits"] + 16 * stats["sphere_tests"] + 32 * n_local   # 128-byte 4-wide nodes
-    traffic = None
+    traffic, issue = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("k_trace_primary_packet", {}).get("dram_bytes_per_launch")
+            rec = json.load(f).get("k_trace_primary_packet", {})
+        traffic = rec.get("dram_bytes_per_launch")
+        if rec.get("warp_inst_per_launch") and W == WIDTH and H == HEIGHT and args.spheres == N_SPHERES:
+            # the kernel's real bound (FP32 issue): warp instructions of one launch (ncu) over the issue slots
+            # of the timed launch, 4 schedulers x SM count x SM clock
+            slots = 4.0 * peaks["sm_count"] * (clk.get("sm_mhz") or sm_max) * 1e6
+            issue = {"warp_inst_per_launch": rec["warp_inst_per_launch"], "issue_slots_per_s": slots,
+                     "frac": rec["warp_inst_per_launch"] / k_s / slots, "ncu_issue_active_pct": rec.get("issue_active_pct_ncu"),
+                     "source": rec.get("inst_source")}
     roofline = {
         "kernel": "k_trace_primary_packet", "bound": "hbm",
         "achieved": compulsory_bytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -441,6 +449,7 @@ def run_b200(args):
                 "(128 B per 4-wide node, 16 B/sphere) read once; the ncu profile shows the kernel is instruction-issue bound, "
                 "not HBM bound (profiles/)",
         "kernel_ms": k_ms,
+        "issue_bound": issue,
         "tile_work": {"tiles": tiles, "nodes_popped_per_tile": stats["inner_visits"] / tiles,
                       "sphere_tests_per_ray": stats["sphere_tests"] / n_local,
                       "exact_leaf_box_tests_per_ray": stats["exact_box_tests"] / n_local,

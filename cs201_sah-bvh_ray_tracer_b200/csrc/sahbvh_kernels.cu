@@ -246,10 +246,13 @@ k_trace_rays_coop(const float *__restrict__ nodes, const float *__restrict__ sph
 __device__ __forceinline__ void ld_wide_node(const uint32_t *__restrict__ nodes, int32_t node, uint32_t (&w)[16])
 {
     const uint32_t *p = nodes + (size_t)node * 16;
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef WIDE_LD
+#define WIDE_LD "ld.global.nc.v8.b32"
+#endif
+    asm volatile(WIDE_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                  : "l"(p));
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile(WIDE_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
                  : "l"(p + 8));
 }

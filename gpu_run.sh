@@ -1,10 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-N=${1:-2}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "exit $?"
-tail -3 gpurun_out/bench_n$N.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench_n$N.json').read().strip().splitlines()[-1])
-print('N',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'], d.get('render_path'), d['config'].get('assembled_frame_check'), d['clocks'])
-PY
+echo base; python tools/bounce_bench.py --modes 2 --steps 5 2>&1 | grep "mode 2"
+for v in A B C; do echo "variant $v"; SAHBVH_LIB=$PWD/cs201_sah-bvh_ray_tracer_b200/build/var_$v.so python tools/bounce_bench.py --modes 2 --steps 5 2>&1 | grep "mode 2"; done
