@@ -436,22 +436,27 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (width + 15) >> 4, tiles_y = (y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H;
-    const long long tile = (long long)blockIdx.x * PKT_WARPS + warp;
+    const unsigned tile = blockIdx.x * PKT_WARPS + warp;   /* < 2^31: the launch rejects larger frames */
     SahCounters cnt = {0, 0, 0, 0};
     unsigned long long hits = 0;
-    if (tile < (long long)tiles_x * tiles_y) {
+    if (tile < (unsigned)tiles_x * (unsigned)tiles_y) {
         int32_t *stack = s_stack[warp];
-        const int tx = (int)(tile % tiles_x), ty = (int)(tile / tiles_x);
+        const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile - (unsigned)ty * (unsigned)tiles_x);
         /* ---- this lane's 4 rays: pixel (tx*16 + (k&1)*8 + lane%8, y0 + ty*8 + (k>>1)*4 + lane/8) ---- */
         const int px0 = tx * 16 + (lane & 7), py0 = y0 + ty * PKT_TILE_H + (lane >> 3);
         unsigned valid = 0;
         float lminx = INFINITY, lminy = INFINITY, lminz = INFINITY, lmaxx = -INFINITY, lmaxy = -INFINITY, lmaxz = -INFINITY;
         float lmin_a = INFINITY;
+        /* the lane's rays use 2 distinct columns and PKT_K/2 distinct rows: one division each (main.c:362-363) */
+        const float u0 = sah_pixel_u(cam, px0), u1 = sah_pixel_u(cam, px0 + 8);
+        float vrow[PKT_K / 2];
+#pragma unroll
+        for (int q = 0; q < PKT_K / 2; q++) vrow[q] = sah_pixel_v(cam, py0 + q * 4);
 #pragma unroll kPktUnroll
         for (int k = 0; k < PKT_K; k++) {
             const int px = px0 + (k & 1) * 8, py = py0 + (k >> 1) * 4;
             float dx, dy, dz;
-            sah_primary_dir(cam, px, py, dx, dy, dz);
+            sah_primary_dir_uv(cam, (k & 1) ? u1 : u0, vrow[k >> 1], dx, dy, dz);
             const float ra = F_ADD(F_ADD(F_MUL(dx, dx), F_MUL(dy, dy)), F_MUL(dz, dz));
             s_ray[warp][k][0][lane] = dx; s_ray[warp][k][1][lane] = dy; s_ray[warp][k][2][lane] = dz; s_ray[warp][k][3][lane] = ra;
             s_bt[warp][k][lane] = 0.0f;
@@ -1099,6 +1104,10 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
     const SahScene sc = sahbvh_make_scene(b->info);
     if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
         long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H);
+        if (tiles >= (1ll << 31) - PKT_WARPS) {
+            sahbvh_set_error("frame too large for one launch (%lld tiles): trace it in row bands", tiles);
+            return SAHBVH_E_ARG;
+        }
         unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
         if (count)
             k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,

@@ -606,6 +606,19 @@ struct SahCamera {
     float fw, fh;              /* (float)W, (float)H */
 };
 
+/* main.c:362-363: the two pixel coordinates the camera ray is built from (v already negated, main.c:365) */
+SAH_HD float sah_pixel_u(const SahCamera &c, int x) { return F_MUL(F_SUB(F_DIV((float)x, c.fw), 0.5f), c.aspect); }
+SAH_HD float sah_pixel_v(const SahCamera &c, int y) { return -F_SUB(F_DIV((float)y, c.fh), 0.5f); }
+
+/* ray.c:26-31 for (u, v): direction only (origin = position) */
+SAH_HD void sah_primary_dir_uv(const SahCamera &c, float u, float v, float &dx, float &dy, float &dz) {
+    float ax = F_ADD(c.fx, F_MUL(c.hx, u)), ay = F_ADD(c.fy, F_MUL(c.hy, u)), az = F_ADD(c.fz, F_MUL(c.hz, u));
+    ax = F_ADD(ax, F_MUL(c.vx, v)); ay = F_ADD(ay, F_MUL(c.vy, v)); az = F_ADD(az, F_MUL(c.vz, v));
+    float len = F_SQRT(F_ADD(F_ADD(F_MUL(ax, ax), F_MUL(ay, ay)), F_MUL(az, az)));
+    if (len != 0.0f) { dx = F_DIV(ax, len); dy = F_DIV(ay, len); dz = F_DIV(az, len); }
+    else { dx = 0.0f; dy = 0.0f; dz = 0.0f; }
+}
+
 /* main.c:362-365 + ray.c:26-31 for pixel (x,y): direction only (origin = position) */
 SAH_HD void sah_primary_dir(const SahCamera &c, int x, int y, float &dx, float &dy, float &dz) {
     float u = F_MUL(F_SUB(F_DIV((float)x, c.fw), 0.5f), c.aspect);
