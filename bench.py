@@ -288,11 +288,40 @@ def run_b200(args):
     n_local = rows * W
     total_rays = W * H
     hits_local = torch.empty((n_local, 8), dtype=torch.float32, device="cuda")          # this rank's 32-byte records
-    # frame assembly (N > 1): all_gather of the 4-byte primitive-id buffer (t, point, normal are pure functions of
-    # the pixel's ray and the hit sphere: gpu_hits_from_prims_dev rebuilds bit-identical records wherever they are
-    # needed); the kernel writes this rank's band straight into its slot; double-buffered so gather k overlaps kernel k+1
-    ids = [torch.empty((world, n_local), dtype=torch.int32, device="cuda") for _ in range(2)] if dist_on else None
+    # frame assembly (N > 1).  Default: FUSED -- rank 0 owns the frame's 4-byte primitive-id buffer (t, point, normal are
+    # pure functions of the pixel's ray and the hit sphere: gpu_hits_from_prims_dev rebuilds bit-identical records from
+    # the ids), the other ranks map it through CUDA IPC and every rank's trace kernel stores its band straight into it
+    # over NVLink peer memory while it computes; an 8-byte all_reduce per frame on a side stream is the "frame complete"
+    # barrier.  Fallback (peer mapping unavailable): NCCL all_gather of the id buffer, double-buffered under the next kernel.
     comm = torch.cuda.Stream() if dist_on else None
+    ids, fb_ptrs, fb_owned, assembly = None, None, None, None
+    if dist_on:
+        ok = 1
+        handles = [None, None]
+        try:
+            if rank == 0:
+                fb_owned = [pkg.peer_alloc(world * n_local * 4, local) for _ in range(2)]
+                handles = [h for _, h in fb_owned]
+        except Exception:
+            ok = 0
+        dist.broadcast_object_list(handles, src=0)
+        try:
+            if rank == 0:
+                fb_ptrs = [p for p, _ in fb_owned] if fb_owned else None
+            elif handles[0] is not None:
+                fb_ptrs = [pkg.peer_open(h, local) for h in handles]
+            if fb_ptrs is None:
+                ok = 0
+        except Exception:
+            ok = 0
+        tok = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(tok, op=dist.ReduceOp.MIN)
+        if int(tok.item()) == 1:
+            assembly = "peer"
+            flag = torch.zeros(1, dtype=torch.int64, device="cuda")
+        else:
+            assembly = "all_gather"
+            ids = [torch.empty((world, n_local), dtype=torch.int32, device="cuda") for _ in range(2)]
 
     def run_steps(k_steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -301,15 +330,22 @@ def run_b200(args):
         for k in range(k_steps):
             flush()
             if dist_on:
-                buf = ids[k & 1]
                 if gather_done[k & 1] is not None:
                     main_stream.wait_event(gather_done[k & 1])
-                bvh.trace_primary_dev_prims(cam, W, H, y0, y1, hits_local.data_ptr(), buf[rank].data_ptr(), stream)
+                if assembly == "peer":
+                    dst = fb_ptrs[k & 1] + rank * n_local * 4
+                else:
+                    buf = ids[k & 1]
+                    dst = buf[rank].data_ptr()
+                bvh.trace_primary_dev_prims(cam, W, H, y0, y1, hits_local.data_ptr(), dst, stream)
                 ek = torch.cuda.Event()
                 ek.record(main_stream)
                 with torch.cuda.stream(comm):
                     comm.wait_event(ek)
-                    dist.all_gather_into_tensor(buf.view(world * n_local), buf[rank])
+                    if assembly == "peer":
+                        dist.all_reduce(flag)                  # every rank's kernel k is complete: frame k is whole on rank 0
+                    else:
+                        dist.all_gather_into_tensor(buf.view(world * n_local), buf[rank])
                     gd = torch.cuda.Event()
                     gd.record(comm)
                     gather_done[k & 1] = gd
@@ -361,17 +397,21 @@ def run_b200(args):
         render_multi = {"workload": f"path loop (renderer.c:21-76), {W}x{H}, MAX_DEPTH 5, 1 spp, row bands + NCCL all_gather of the RGBA8 frame",
                         "ms_per_frame": float(tr.item()), "value": total_rays / (float(tr.item()) * 1e-3) / 1e9, "unit": "Gpaths/s"}
     if dist_on:
-        # untimed check of the assembled frame: the records rebuilt from the gathered ids of the NEXT rank's band must
-        # equal what that rank traced (exchanged here through one more all_gather of a 64 K-pixel sample)
-        nxt = (rank + 1) % world
-        ny0, ny1 = pkg.shard_rows(H, nxt, world)
-        rebuilt = torch.empty((n_local, 8), dtype=torch.float32, device="cuda")
-        bvh.hits_from_prims_dev(cam, W, H, ny0, ny1, ids[(args.steps - 1) & 1][nxt].data_ptr(), rebuilt.data_ptr(), stream)
-        torch.cuda.synchronize()
+        # untimed check of the assembled frame: the records rebuilt from the assembled ids of another rank's band must
+        # equal what that rank traced (a 64 K-pixel sample per rank, exchanged through one all_gather)
         m = min(n_local, 1 << 16)
         sample = [torch.empty((m, 8), dtype=torch.float32, device="cuda") for _ in range(world)]
         dist.all_gather(sample, hits_local[:m].contiguous())
-        ok = bool((sample[nxt].view(torch.int32) == rebuilt[:m].view(torch.int32)).all().item())
+        last = (args.steps - 1) & 1
+        rebuilt = torch.empty((n_local, 8), dtype=torch.float32, device="cuda")
+        ok = True
+        checks = range(1, world) if (assembly == "peer" and rank == 0) else ([] if assembly == "peer" else [(rank + 1) % world])
+        for r in checks:
+            ry0, ry1 = pkg.shard_rows(H, r, world)
+            src = fb_ptrs[last] + r * n_local * 4 if assembly == "peer" else ids[last][r].data_ptr()
+            bvh.hits_from_prims_dev(cam, W, H, ry0, ry1, src, rebuilt.data_ptr(), stream)
+            torch.cuda.synchronize()
+            ok = ok and bool((sample[r].view(torch.int32) == rebuilt[:m].view(torch.int32)).all().item())
         tok = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
         dist.all_reduce(tok, op=dist.ReduceOp.MIN)
         assembled_ok = bool(tok.item())
@@ -412,6 +452,10 @@ def run_b200(args):
 
     if rank != 0:
         if dist_on:
+            if assembly == "peer":
+                torch.cuda.synchronize()
+                for p in fb_ptrs:
+                    pkg.peer_close(p, local)
             dist.barrier()
             dist.destroy_process_group()
         return
@@ -489,9 +533,11 @@ def run_b200(args):
                    "l2": "160 MiB device memset before every timed step (inside the timed region, ~25 us)",
                    "timing": "one CUDA-event pair around the K steps on the launch stream, max over ranks",
                    "parallelism": f"rays sharded in {world} contiguous row band(s), BVH replicated" +
-                                  (", NCCL all_gather of the frame's primitive-id buffer (4 B/pixel) on a side stream, "
-                                   "double-buffered so gather k overlaps kernel k+1; the kernel writes each rank's band "
-                                   "straight into its all_gather slot" if dist_on else "")},
+                                  ((", frame assembly fused into the trace kernel: every rank stores its band's 4-byte primitive ids straight "
+                                    "into rank 0's frame buffer over NVLink peer memory (CUDA IPC mapping), one 8-byte all_reduce per "
+                                    "frame as the completion barrier" if assembly == "peer" else
+                                    ", NCCL all_gather of the frame's primitive-id buffer (4 B/pixel) on a side stream, double-buffered "
+                                    "so gather k overlaps kernel k+1") if dist_on else "")},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 64 * world, "d2h_bytes_per_step": 32 * total_rays,
                 "api": "gpu_trace_primary (pinned host output buffer per rank); the only input is the 64-byte Camera"},
@@ -503,7 +549,7 @@ def run_b200(args):
     if render_multi is not None:
         line["render_path"] = render_multi
     if assembled_ok is not None:
-        line["config"]["assembled_frame_check"] = ("records rebuilt from the gathered ids == the owning rank's traced records "
+        line["config"]["assembled_frame_check"] = ("records rebuilt from the assembled ids == the owning rank's traced records "
                                                    "(bit-exact, 64 K-pixel sample per rank): " + ("pass" if assembled_ok else "FAIL"))
     print(json.dumps(line), flush=True)
     if dist_on:

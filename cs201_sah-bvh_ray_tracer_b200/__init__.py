@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
     "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
     "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree", "gpu_bvh_download",
+    "sahbvh_peer_alloc", "sahbvh_peer_open", "sahbvh_peer_close", "sahbvh_peer_free",
     "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
@@ -372,6 +373,29 @@ class GpuBvh:
         _check(lib.gpu_trace_primary_stats(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
                                            C.c_void_p(d_out), C.byref(st)), "gpu_trace_primary_stats")
         return st.as_dict()
+
+
+def peer_alloc(nbytes: int, device: int = -1) -> tuple[int, bytes]:
+    """sahbvh_peer_alloc: (device pointer, 64-byte IPC handle) of a buffer other processes' kernels can store into."""
+    p = C.c_void_p()
+    h = (C.c_ubyte * 64)()
+    _check(lib.sahbvh_peer_alloc(C.c_int(device), C.c_size_t(nbytes), C.byref(p), h), "sahbvh_peer_alloc")
+    return int(p.value), bytes(h)
+
+
+def peer_open(handle: bytes, device: int = -1) -> int:
+    p = C.c_void_p()
+    h = (C.c_ubyte * 64).from_buffer_copy(handle)
+    _check(lib.sahbvh_peer_open(C.c_int(device), h, C.byref(p)), "sahbvh_peer_open")
+    return int(p.value)
+
+
+def peer_close(ptr: int, device: int = -1):
+    _check(lib.sahbvh_peer_close(C.c_int(device), C.c_void_p(ptr)), "sahbvh_peer_close")
+
+
+def peer_free(ptr: int, device: int = -1):
+    _check(lib.sahbvh_peer_free(C.c_int(device), C.c_void_p(ptr)), "sahbvh_peer_free")
 
 
 def accumulate(accum: np.ndarray, frames: int, rgba: np.ndarray) -> np.ndarray:

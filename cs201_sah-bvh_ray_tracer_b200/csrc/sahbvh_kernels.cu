@@ -1432,6 +1432,71 @@ extern "C" int gpu_benchmark_with_bvh(gpu_bvh *b, const Ray *rays, int64_t n, in
     return SAHBVH_OK;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* peer framebuffer: the trace kernel of every rank stores its band straight into ONE GPU's frame  */
+/* ------------------------------------------------------------------------------------------ */
+static_assert(sizeof(sahbvh_ipc_handle) == sizeof(cudaIpcMemHandle_t), "IPC handle size");
+
+extern "C" int sahbvh_peer_alloc(int device, size_t bytes, void **d_ptr, sahbvh_ipc_handle *handle)
+{
+    if (!d_ptr || !handle || bytes == 0) {
+        sahbvh_set_error("sahbvh_peer_alloc: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    *d_ptr = nullptr;
+    if (sahbvh_device_count() == 0) {
+        sahbvh_set_error("no usable CUDA device");
+        return SAHBVH_E_CUDA;
+    }
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    void *p = nullptr;
+    CU_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        sahbvh_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return SAHBVH_E_CUDA;
+    }
+    memcpy(handle, &h, sizeof h);
+    *d_ptr = p;
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_peer_open(int device, const sahbvh_ipc_handle *handle, void **d_ptr)
+{
+    if (!d_ptr || !handle) {
+        sahbvh_set_error("sahbvh_peer_open: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    *d_ptr = nullptr;
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CU_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_peer_close(int device, void *d_ptr)
+{
+    if (!d_ptr) return SAHBVH_OK;
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    CU_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_peer_free(int device, void *d_ptr)
+{
+    if (!d_ptr) return SAHBVH_OK;
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    CU_TRY(cudaFree(d_ptr));
+    return SAHBVH_OK;
+}
+
 static int read_counters(gpu_bvh *b, uint64_t rays, gpu_trace_stats *stats)
 {
     unsigned long long h[8];

@@ -130,6 +130,16 @@ int gpu_trace_primary_dev_prims(gpu_bvh *bvh, const Camera *cam, int width, int 
                                 void *d_out, void *d_prims, void *stream);
 int gpu_hits_from_prims_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
                             const void *d_prims, void *d_out, void *stream);
+/* Multi-GPU frame assembly without a separate collective: one GPU (the root) allocates the frame's id buffer
+ * with sahbvh_peer_alloc and hands the 64-byte handle to the other processes (any byte transport); they map it
+ * with sahbvh_peer_open and pass  mapped + band offset  as d_prims to gpu_trace_primary_dev_prims.  The trace
+ * kernel's own 4-byte stores then travel over NVLink / NVSwitch peer memory while it computes, and the frame
+ * is complete on the root when the ranks' kernels are (one small cross-rank barrier per frame). */
+typedef struct sahbvh_ipc_handle { unsigned char bytes[64]; } sahbvh_ipc_handle;
+int sahbvh_peer_alloc(int device, size_t bytes, void **d_ptr, sahbvh_ipc_handle *handle);
+int sahbvh_peer_open(int device, const sahbvh_ipc_handle *handle, void **d_ptr);
+int sahbvh_peer_close(int device, void *d_ptr);   /* for pointers from sahbvh_peer_open */
+int sahbvh_peer_free(int device, void *d_ptr);    /* for pointers from sahbvh_peer_alloc */
 /* Which kernel gpu_trace_primary* launches (process-wide; both give identical hit records):
  *   SAHBVH_PRIMARY_PACKET  (default) one warp per 16x8 pixel tile, interior culling once per tile
  *   SAHBVH_PRIMARY_PER_RAY one thread per pixel, per-ray stack traversal (the ray-buffer kernel's core) */

@@ -716,3 +716,47 @@ def test_10m_config5_scale(gpu):
         gpu.set_build_mode(gpu.BUILD_DEVICE)
         gpu.set_primary_mode(gpu.PRIMARY_PACKET)
         gpu.set_ray_mode(gpu.RAYS_WIDE)
+
+
+def test_peer_frame_buffer_between_processes(gpu, tmp_path):
+    """Fused multi-GPU frame assembly: another PROCESS maps this process's id buffer (CUDA IPC) and its trace kernel
+    stores the band's primitive ids straight into it; the records rebuilt here from those ids equal our own trace.
+    (Both processes share GPU 0 here; bench.py --gpus N runs the same calls across NVLink.)"""
+    import subprocess
+    import sys
+    import torch
+    from common import ROOT
+    n, W, H, y0, y1 = 20000, 1280, 720, 96, 480
+    ptr, handle = gpu.peer_alloc(W * (y1 - y0) * 4)
+    script = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+import __graft_entry__ as g
+import torch
+pkg = g.load_pkg()
+pkg.srand(33)
+s = pkg.benchmark_scene({n})
+bvh = pkg.GpuBvh.build(s, {n}, 0, {n}, 0)
+dst = pkg.peer_open(bytes.fromhex({handle.hex()!r}))
+scratch = torch.empty(({W} * ({y1} - {y0}), 8), dtype=torch.float32, device="cuda")
+bvh.trace_primary_dev_prims(pkg.default_camera(), {W}, {H}, {y0}, {y1}, scratch.data_ptr(), dst, torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+pkg.peer_close(dst)
+print("child ok")
+"""
+    try:
+        out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "child ok" in out.stdout, out.stderr[-2000:]
+        gpu.srand(33)
+        s = gpu.benchmark_scene(n)
+        bvh = gpu.GpuBvh.build(s, n, 0, n, 0)
+        cam = gpu.default_camera()
+        want = bvh.trace_primary(cam, W, H, y0, y1)
+        rebuilt = torch.empty((W * (y1 - y0), 8), dtype=torch.float32, device="cuda")
+        bvh.hits_from_prims_dev(cam, W, H, y0, y1, ptr, rebuilt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert_hits_equal(rebuilt.cpu().numpy().view(HIT_DT).reshape(-1), want, "records rebuilt from the peer-written ids")
+        assert (want["prim"] >= 0).sum() > 1000
+        bvh.close()
+    finally:
+        gpu.peer_free(ptr)
