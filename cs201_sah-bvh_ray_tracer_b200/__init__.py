@@ -67,7 +67,8 @@ class BvhInfo(C.Structure):
 
 class TraceStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("inner_visits", C.c_uint64), ("sphere_tests", C.c_uint64),
-                ("exact_box_tests", C.c_uint64), ("hits", C.c_uint64), ("max_stack", C.c_uint64)]
+                ("exact_box_tests", C.c_uint64), ("hits", C.c_uint64), ("max_stack", C.c_uint64),
+                ("max_visits", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

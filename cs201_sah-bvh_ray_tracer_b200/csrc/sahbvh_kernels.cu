@@ -282,6 +282,7 @@ k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ 
     long long chunk_next = 0, chunk_end = 0; /* warp-uniform */
     bool more = true;                        /* warp-uniform: the global pool may still have rays */
     unsigned dead = 0;                       /* warp-uniform: lanes that will get no more rays */
+    unsigned long long visits0 = 0;          /* COUNT: cnt.inner when this lane's ray started */
     int thresh = WIDE_REFILL_MIN;            /* warp-uniform: waiting lanes that trigger a service round */
     static_assert(SAH_NODE_DONE == -1, "lane state encoding");
 
@@ -306,6 +307,7 @@ k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ 
                 }
                 store_hit(out + ray_idx, h);
                 ray_idx = -1;
+                if (COUNT) atomicMax(&counters[5], cnt.inner - visits0);
             }
             /* 3. free lanes take new rays */
             const unsigned idle = __ballot_sync(full, node == SAH_NODE_DONE);
@@ -333,6 +335,7 @@ k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ 
                     best_t = 0.0f; best_s = INFINITY; best_prim = -1;
                     sp = 0;
                     node = 0;
+                    if (COUNT) visits0 = cnt.inner;
                 }
                 chunk_next += take;
             }
@@ -1507,6 +1510,7 @@ static int read_counters(gpu_bvh *b, uint64_t rays, gpu_trace_stats *stats)
     stats->exact_box_tests = h[2];
     stats->hits = h[3];
     stats->max_stack = h[4];
+    stats->max_visits = h[5];
     return SAHBVH_OK;
 }
 

@@ -9,13 +9,14 @@
  * Interior boxes only cull (a leaf's exact test passing implies every ancestor's passes, Q7),
  * so inner nodes use a cheaper CONSERVATIVE slab test:
  *
- *   t = fma(plane, inv_d, -o*inv_d)                     1 FFMA per plane
+ *   t = fma(plane, inv_d, -o*inv_d -+ e)                1 FFMA per plane
  *   |t - t_ref| <= 4u|t_ref| + u|o*inv_d|               (u = 2^-24; the product plane*inv_d is
  *                                                        exact inside the FMA, only o*inv_d and
  *                                                        inv_d itself are rounded)
- *   pass  <=>  max(tnear, 0) <= min(tfar*(1+2^-20) + A2, best_s)
- *   A2     =  2^-20 * max_axis |o*inv_d|                 (>= 4x the bound, both sides)
- *   best_s =  best_t*(1+2^-9) + 2*r_max/|d| + A2         cull slack: the reference's float
+ *   e      =  2^-20 |o*inv_d| per axis, subtracted from the NEAR plane's addend and added to the
+ *             FAR plane's (>= 15x the absolute part of the bound after its own rounding)
+ *   pass  <=>  max(tnear, 0) <= min(tfar*(1+2^-20), best_s)
+ *   best_s =  best_t*(1+2^-9) + 2*r_max/|d|              cull slack: the reference's float
  *             discriminant can move the computed t by <= 1.0e-3*|oc|/|d| and a float-noise
  *             "hit" of a far sphere can sit <= sqrt(2)*r/|d| before its own box entry.
  *   Axes with |d| < 1e-30 (incl. the reference's d==0 rule) or a non-finite o*inv_d are
@@ -85,8 +86,7 @@ struct SahRay {
     float nx, ny, nz;      /* addend of the LO plane: -(o*inv)            [geometric: -(o+pad)*2^100] */
     float mx, my, mz;      /* addend of the HI plane: same as n*           [geometric: -(o-pad)*2^100] */
     float a;               /* d.d in the reference's order (hit.c:22) */
-    float a2;              /* absolute slack of the conservative box test */
-    float cull_abs;        /* 2*r_max/|d| + a2 */
+    float cull_abs;        /* 2*r_max/|d| */
 };
 
 /* per-tree constants the ray set-up needs */
@@ -98,7 +98,7 @@ struct SahScene {
 };
 
 struct SahCounters {
-    unsigned long long inner, spheres, exact, max_stack;
+    unsigned long long inner, spheres, exact, max_stack, max_visits;
 };
 
 SAH_HD float sah_nan() {
@@ -129,20 +129,27 @@ SAH_HD float sah_nan() {
  */
 SAH_HD void sah_axis_setup(float o, float d, float pad, bool geometric, float &inv, float &n_lo, float &n_hi, float &slack_src) {
     const float big = 1.2676506002282294e30f; /* 2^100 */
+    slack_src = 0.0f;
     if (fabsf(d) >= SAH_TINY_DIR) {
         float i = F_DIV(1.0f, d);
         float n = -F_MUL(o, i);
         bool ok = fabsf(n) <= 3.0e38f;
+        /* the absolute error u|o*inv| of this axis' plane distances is covered HERE, per axis, by moving the
+         * near plane's addend down and the far plane's up by 2^-20 |o*inv| (lo is the near plane iff inv >= 0).
+         * A single slack max_a|o_a*inv_a| on the final comparison would let one tiny direction component
+         * (|d_a| ~ 1e-6 gives |o*inv| ~ 1e8) switch off the culling of the other two axes: such rays were
+         * measured at 35x the average node count, and a handful of them set the tail of every launch. */
+        float e = F_MUL(fabsf(n), SAH_ABS_SCALE);
+        bool lo_near = i >= 0.0f;
         inv = ok ? i : sah_nan();
-        n_lo = n_hi = ok ? n : sah_nan();
-        slack_src = ok ? fabsf(n) : 0.0f;
+        n_lo = ok ? (lo_near ? F_SUB(n, e) : F_ADD(n, e)) : sah_nan();
+        n_hi = ok ? (lo_near ? F_ADD(n, e) : F_SUB(n, e)) : sah_nan();
     } else {
         float a = -F_MUL(F_ADD(o, pad), big), b = -F_MUL(F_SUB(o, pad), big);
         bool ok = geometric && fabsf(a) <= 3.0e38f && fabsf(b) <= 3.0e38f;
         inv = ok ? big : sah_nan();
         n_lo = ok ? a : sah_nan();
         n_hi = ok ? b : sah_nan();
-        slack_src = 0.0f;
     }
 }
 
@@ -161,11 +168,11 @@ SAH_HD void sah_ray_setup(SahRay &r, float ox, float oy, float oz, float dx, flo
     sah_axis_setup(oy, dy, pad, geo, r.iy, r.ny, r.my, sy);
     sah_axis_setup(oz, dz, pad, geo, r.iz, r.nz, r.mz, sz);
     r.a = F_ADD(F_ADD(F_MUL(dx, dx), F_MUL(dy, dy)), F_MUL(dz, dz));
-    r.a2 = fmaxf(fmaxf(sx, sy), sz) * SAH_ABS_SCALE;
+    (void)sx; (void)sy; (void)sz;
     /* 2*r_max/|d|; |d| from the same float sum (exactness irrelevant: slack only) */
     float len = sqrtf(r.a);
     float per_d = (len > 0.0f) ? (2.0f * sc.r_max) / len : INFINITY;
-    r.cull_abs = per_d + r.a2;
+    r.cull_abs = per_d;
 }
 
 /* conservative slab test of one box; returns entry distance through tnear */
@@ -177,7 +184,7 @@ SAH_HD bool sah_box_conservative(const SahRay &r, float lox, float loy, float lo
     float tn = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
     float tf = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
     tn = fmaxf(tn, 0.0f);
-    tf = fminf(F_FMA(tf, SAH_REL_BOX, r.a2), best_s);
+    tf = fminf(F_MUL(tf, SAH_REL_BOX), best_s);
     tnear = tn;
     return tn <= tf;
 }
@@ -341,7 +348,7 @@ SAH_HD void sah_trace_one(const float *__restrict__ nodes, const float *__restri
  *                      A_lo  = fma(p, inv, n_lo),  A_hi = fma(p, inv, n_hi)
  * per child plane:     t     = fma(1024 + q, s_inv, A)  1024 + q exact in fp16 and fp32
  * Against the true t of the DECODED plane the error is
- *     <= 4u|t| + u|o*inv|          (as for sah_box_conservative: covered by SAH_REL_BOX and a2)
+ *     <= 4u|t| + u|o*inv|          (as for sah_box_conservative: covered by SAH_REL_BOX and the per-axis addend slack)
  *      + u|A| + u|(1024+q)*s_inv|  (the intermediate A can be as large as |t| + 1279|s_inv|)
  *     <= ... + 2^-13 |s_inv|,
  * i.e. 2^-13 of a grid cell in t-space; the decoded box contains the true child box with a
@@ -493,7 +500,7 @@ SAH_UNROLL
         const float tny = F_FMA(fny[c], sy, any_), tfy = F_FMA(ffy[c], sy, afy);
         const float tnz = F_FMA(fnz[c], sz, anz), tfz = F_FMA(ffz[c], sz, afz);
         tn[c] = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.0f);
-        const float f_ = fminf(F_FMA(fminf(fminf(tfx, tfy), tfz), SAH_REL_BOX, r.a2), best_s);
+        const float f_ = fminf(F_MUL(fminf(fminf(tfx, tfy), tfz), SAH_REL_BOX), best_s);
         /* an absent child (SAH_REF_NONE, inverted grid box) can pass only when every axis is
          * ignored; it then looks like a special leaf with an out-of-range index and is skipped */
         hit[c] = tn[c] <= f_;

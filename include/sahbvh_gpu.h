@@ -60,6 +60,7 @@ typedef struct gpu_trace_stats {
     uint64_t exact_box_tests;
     uint64_t hits;
     uint64_t max_stack;
+    uint64_t max_visits;     /* most nodes any single ray fetched (ray-buffer kernel over the wide tree; 0 elsewhere) */
 } gpu_trace_stats;
 
 const char *sahbvh_last_error(void);

@@ -88,14 +88,14 @@ class HostEmul:
     def trace(self, h, rays, threads=8, tree=None, fast_depth=16, drain_every=7):
         rays = np.ascontiguousarray(rays)
         hits = np.zeros(len(rays), HIT_DT)
-        st = (C.c_uint64 * 6)()
+        st = (C.c_uint64 * 7)()
         if (tree or self.tree) == "wide":
             rc = self.lib.emul_wide_trace(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), _ptr(hits), st, C.c_int(threads),
                                           C.c_int(fast_depth), C.c_int(drain_every))
             assert rc == 0
         else:
             self.lib.emul_trace(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), _ptr(hits), st, C.c_int(threads))
-        stats = dict(zip(("rays", "inner_visits", "sphere_tests", "exact_box_tests", "hits", "max_stack"), map(int, st)))
+        stats = dict(zip(("rays", "inner_visits", "sphere_tests", "exact_box_tests", "hits", "max_stack", "max_visits"), map(int, st)))
         return hits, stats
 
     def primary_rays(self, cam, w, h, y0=0, y1=None):

@@ -101,7 +101,7 @@ static void trace_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t 
 extern "C" void emul_trace(const emul_bvh *e, const Ray *rays, int64_t n, gpu_hit *out, gpu_trace_stats *stats, int threads)
 {
     if (threads < 1) threads = 1;
-    std::vector<SahCounters> cnt((size_t)threads, SahCounters{0, 0, 0, 0});
+    std::vector<SahCounters> cnt((size_t)threads, SahCounters{0, 0, 0, 0, 0});
     std::vector<std::thread> pool;
     for (int k = 0; k < threads; k++)
         pool.emplace_back(trace_range, e, rays, n * k / threads, n * (k + 1) / threads, out, &cnt[(size_t)k]);
@@ -307,7 +307,9 @@ static void wide_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t h
         sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
                       rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, sc);
         SahHit h;
+        const unsigned long long before = cnt->inner;
         sah_wide_trace_one<true>(e->w.nodes, e->f.spheres4, e->w.special, e->f.info.n_spheres, e->w.n_special, r, stk, drain_every, h, cnt);
+        if (cnt->inner - before > cnt->max_visits) cnt->max_visits = cnt->inner - before;
         memcpy(&out[i], &h, sizeof h);
     }
 }
@@ -318,7 +320,7 @@ extern "C" int emul_wide_trace(emul_bvh *e, const Ray *rays, int64_t n, gpu_hit 
     int rc = ensure_wide(e);
     if (rc != SAHBVH_OK) return rc;
     if (threads < 1) threads = 1;
-    std::vector<SahCounters> cnt((size_t)threads, SahCounters{0, 0, 0, 0});
+    std::vector<SahCounters> cnt((size_t)threads, SahCounters{0, 0, 0, 0, 0});
     std::vector<std::thread> pool;
     for (int k = 0; k < threads; k++)
         pool.emplace_back(wide_range, e, rays, n * k / threads, n * (k + 1) / threads, out, &cnt[(size_t)k], fast_depth,
@@ -332,6 +334,7 @@ extern "C" int emul_wide_trace(emul_bvh *e, const Ray *rays, int64_t n, gpu_hit 
             stats->sphere_tests += c.spheres;
             stats->exact_box_tests += c.exact;
             if (c.max_stack > stats->max_stack) stats->max_stack = c.max_stack;
+            if (c.max_visits > stats->max_visits) stats->max_visits = c.max_visits;
         }
         for (int64_t i = 0; i < n; i++) stats->hits += out[i].prim >= 0;
     }

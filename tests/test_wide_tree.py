@@ -145,3 +145,39 @@ def test_special_leaves_of_degenerate_trees(oracle, wide, golden, seed):
         from common import sha
         assert sha(got) == case["sha_hits"]
     wide.free(h)
+
+
+def test_tiny_direction_component_does_not_disable_culling(oracle):
+    """A ray with one direction component of 1e-5..1e-25 has |o*inv| ~ 1e7..1e27 on that axis.  The absolute slack
+    for that term must stay on that axis (it is folded into the near/far plane addends): applied to the whole
+    comparison it would accept every box within ~|o*inv| * 2^-20 and the ray would walk most of the tree."""
+    from common import HostEmul
+    oracle.srand(1)
+    n = 60000
+    s = oracle.scene_benchmark(n)
+    so = s.copy()
+    nodes = oracle.build(so, 0, n, 0)
+    rng = np.random.default_rng(5)
+    m = 4000
+    rays = np.zeros(m, RAY_DT)
+    rays["o"] = rng.uniform(-450, 450, size=(m, 3)).astype(np.float32)
+    d = rng.normal(size=(m, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    axis = rng.integers(0, 3, m)
+    tiny = rng.choice([1e-4, 1e-5, 1e-6, 1e-8, 1e-12, 1e-20, 1e-25, 1e-29], m) * rng.choice([-1.0, 1.0], m)
+    d[np.arange(m), axis] = tiny
+    rays["d"] = d.astype(np.float32)
+    ref_rays = rays.copy()
+    ref_rays["d"] = rng.normal(size=(m, 3)).astype(np.float32)      # ordinary directions from the same origins
+    want, _ = oracle.trace_bvh(nodes, so, n, rays)
+    for tree in ("binary", "wide"):
+        e = HostEmul(tree)
+        h = e.build(s.copy(), n, 0, n, 0)
+        got, st = e.trace(h, rays)
+        assert_hits_equal(got, want, f"tiny direction component ({tree})")
+        _, st_ref = e.trace(h, ref_rays)
+        assert st["inner_visits"] < 2.0 * st_ref["inner_visits"], (tree, st, st_ref)
+        if tree == "wide":
+            assert st["max_visits"] < 6 * st_ref["max_visits"], (st, st_ref)
+        e.free(h)
+    assert (want["prim"] >= 0).sum() > 20

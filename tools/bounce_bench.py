@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--kind", default="bounce", choices=["bounce", "bench", "primary"])
     ap.add_argument("--stride", type=int, default=1, help="generate rays*stride rays and keep every stride-th")
+    ap.add_argument("--sort", default="", choices=["", "morton", "morton_dir", "shuffle"], help="reorder the rays on the host before tracing")
     ap.add_argument("--tile", default="", help="WxH: take the primary hits in pixel-tile order (e.g. 8x4) instead of row-major")
     args = ap.parse_args()
     import torch
@@ -53,6 +54,27 @@ def main():
         rays = pkg.benchmark_rays(args.rays)
     else:
         rays = pkg.generate_primary_rays(cam, W, H)
+    if args.sort:
+        o = rays["o"].astype(np.float64)
+        if args.sort == "shuffle":
+            order = np.random.default_rng(0).permutation(len(rays))
+        else:
+            lo, hi = o.min(axis=0), o.max(axis=0)
+            q = np.clip(((o - lo) / (hi - lo + 1e-9) * 1023).astype(np.uint64), 0, 1023)
+
+            def spread(v):
+                v = (v | (v << 16)) & 0x030000FF
+                v = (v | (v << 8)) & 0x0300F00F
+                v = (v | (v << 4)) & 0x030C30C3
+                v = (v | (v << 2)) & 0x09249249
+                return v
+            key = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+            if args.sort == "morton_dir":
+                d = rays["d"]
+                octant = ((d[:, 0] < 0).astype(np.uint64) | ((d[:, 1] < 0).astype(np.uint64) << 1) | ((d[:, 2] < 0).astype(np.uint64) << 2))
+                key = (octant << 30) | key
+            order = np.argsort(key, kind="stable")
+        rays = np.ascontiguousarray(rays[order])
     n = len(rays)
     d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 6)).cuda()
     ref = None
@@ -77,7 +99,7 @@ def main():
         else:
             same = bool((ref.view(np.uint32) == h.view(np.uint32)).all())
         print(f"mode {mode}: {ms:8.3f} ms  {n / ms / 1e6:7.3f} Grays/s  nodes/ray {st['inner_visits'] / n:6.1f} "
-              f"spheres/ray {st['sphere_tests'] / n:5.2f} max_stack {st['max_stack']} same_as_first {same}", flush=True)
+              f"spheres/ray {st['sphere_tests'] / n:5.2f} max_stack {st['max_stack']} max_visits {st['max_visits']} same_as_first {same}", flush=True)
 
 
 if __name__ == "__main__":
