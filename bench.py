@@ -6,15 +6,17 @@ Headline workload (config.workload): the scene north_star's target is quoted on 
 3840x2160 primary rays of the default camera (main.c:203-211, :356-365), one closest-hit
 query per pixel.  One "step" = one full frame through the fused ray-generation + traversal
 kernel, hit records (32 B/ray) written to HBM.  `sweep` adds the other single-GPU
-configurations (default 20-sphere scene 800x600, 100 K spheres 4K primary, 1 M spheres
-incoherent diffuse-bounce rays) measured the same way.
+configurations (benchmark.c as shipped, default 20-sphere scene 800x600, 100 K spheres 4K primary,
+1 M spheres incoherent diffuse-bounce rays, the depth-5 path loop; --config5: 10 M spheres, 8K x 16 spp)
+measured the same way.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-sweep] [--no-cpu] [--config5]
 
 N > 1: launched under torchrun, one rank per GPU; the BVH is replicated (every rank builds the
 same tree from the same seed), rows are sharded in contiguous bands, every rank traces ITS band
 of a full frame per step ("weak": per-GPU work fixed = one full 4K frame's worth of rows per
-rank, the frame height grows with N) and an NCCL all_gather assembles the frame buffer.
+rank, the frame grows with N) and the frame's primitive-id buffer is assembled on rank 0 by the
+trace kernels themselves (peer stores over NVLink; NCCL all_gather as the fallback).
 """
 from __future__ import annotations
 
