@@ -396,7 +396,9 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
  * (and, for a would-be winner, the reference-exact leaf box test) on each candidate, so the
  * result is the same "best over leaves whose own tests pass" as the per-ray kernel.
  */
+#ifndef PKT_WARPS
 #define PKT_WARPS 4
+#endif
 #define PKT_STACK 512
 #ifndef PKT_K
 #define PKT_K 4 /* rays per lane: tile = 16 x (2*PKT_K) pixels */

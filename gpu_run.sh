@@ -1,5 +1,2 @@
 #!/bin/bash
-mkdir -p gpurun_out
-CMD="python tools/bounce_bench.py --modes 2 --rays 16777216 --steps 1"
-$CMD > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_trace_rays_wide -s 1 -c 1 -f -o gpurun_out/prof_wide_r1 $CMD > gpurun_out/ncu_full.log 2>&1
-echo "ncu exit $?"; tail -1 gpurun_out/plain.log
+for v in A B C; do echo "variant $v"; SAHBVH_LIB=$PWD/cs201_sah-bvh_ray_tracer_b200/build/var_$v.so python tools/primary_bench.py 2>&1 | grep "mode 1"; done
