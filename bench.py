@@ -260,17 +260,6 @@ def run_b200(args):
     if pkg.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the closest-hit path has no CPU fallback")
     torch.cuda.set_device(local)
-    numa = None
-    if dist_on:
-        # one process per GPU: run on the CPUs next to this GPU so that the pinned host buffers of the end-to-end leg
-        # are first-touched on its NUMA node (8 ranks copying 265 MB each per step otherwise meet on one socket)
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-            numa = "cpu affinity of the rank set to its GPU's (NVML)"
-        except Exception as e:
-            numa = f"cpu affinity not set: {e}"
     if dist_on:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -553,8 +542,7 @@ def run_b200(args):
                                     "so gather k overlaps kernel k+1") if dist_on else "")},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 64 * world, "d2h_bytes_per_step": 32 * total_rays,
-                "api": "gpu_trace_primary (pinned host output buffer per rank); the only input is the 64-byte Camera",
-                "host_placement": numa},
+                "api": "gpu_trace_primary (pinned host output buffer per rank); the only input is the 64-byte Camera"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
