@@ -65,7 +65,7 @@ def measured_peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  The timed region is a few milliseconds long, so the
-    sampler polls NVML from a thread every ~1 ms (nvidia-smi -lms cannot go below ~100 ms); it falls back to one
+    sampler polls NVML from a thread every ~3 ms (nvidia-smi -lms cannot go below ~100 ms); it falls back to one
     nvidia-smi query taken while a kernel loop is still in flight when NVML is unavailable."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
@@ -96,7 +96,7 @@ class ClockSampler:
                 self.samples.append((float(mhz), int(mask)))
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.003)
 
     def start(self):
         if self.h is None:
@@ -117,7 +117,7 @@ class ClockSampler:
                 if mask & bit:
                     reasons.add(name)
         return {"sm_mhz": float(np.median([m for m, _ in self.samples])), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(reasons), "samples": len(self.samples), "how": "NVML polled every ~1 ms during the timed steps"}
+                "reasons": sorted(reasons), "samples": len(self.samples), "how": "NVML polled every ~3 ms during the timed steps"}
 
     def _smi_once(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
