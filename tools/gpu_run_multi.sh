@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-N=${1:-2}
+N=${1:-2}   # usage: gpurun --gpus N -- bash tools/gpu_run_multi.sh N
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "exit $?"
 tail -2 gpurun_out/bench_n$N.err
 python - <<PY
