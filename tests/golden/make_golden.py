@@ -134,6 +134,25 @@ def main():
     answers["camera_update"] = {"yaw": -2.6, "pitch": 0.15, "sha_camera": sha(cam), "sha_rays_800x600": sha(R.primary_rays(cam))}
     vec["camera_update__cam"] = cam
 
+    # --- the path loop: main.c:356-366 over trace_ray (renderer.c:21-76), MAX_DEPTH 5, 800x600, and the
+    #     accumulation of main.c:368-405 over three frames
+    R.srand(1)
+    s = R.scene_random(20)
+    root, _ = R.build(s, 0, 20, 0)
+    cam = R.default_camera()
+    frames = []
+    for rep in range(3):
+        R.srand(100 + rep)
+        frames.append(R.render(cam, s, 20, root if rep != 1 else None))
+    acc = np.zeros((800 * 600, 3), np.float32)
+    nfr = np.zeros(1, np.int32)
+    shown = [R.accumulate(acc, nfr, f, first=(k == 0)) for k, f in enumerate(frames)]
+    answers["render_default_seed1"] = {
+        "scene": "srand(1), 20 x create_random_sphere, build(0,20,0)", "frames": "srand(100+k) before frame k; frame 1 brute force (bvh = NULL)",
+        "sha_frames": [sha(f) for f in frames], "sha_shown": [sha(x) for x in shown], "sha_accum": sha(acc),
+        "distinct_colours_frame0": int(len(np.unique(frames[0], axis=0)))}
+    R.free(root)
+
     answers["layout"] = R.layout[:20]
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(answers, f, indent=1, sort_keys=True)

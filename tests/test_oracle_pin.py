@@ -198,3 +198,20 @@ def test_oracle_path_loop_equals_reference_trace_ray(oracle, reflib):
             shown_o = oracle.accumulate(acc_o, k + 1, f)
             assert same(shown_r, shown_o) and same(acc_r, acc_o) and int(nfr[0]) == k + 1
         reflib.free(root)
+
+
+def test_golden_path_loop(oracle, golden):
+    """renderer.c:21-76 + main.c:368-405 against the committed fixture (three 800x600 frames of the default scene)."""
+    answers, _ = golden
+    g = answers["render_default_seed1"]
+    oracle.srand(1)
+    s = oracle.scene_random(20)
+    nodes = oracle.build(s, 0, 20, 0)
+    cam = oracle.default_camera()
+    acc = np.zeros((800 * 600, 3), np.float32)
+    for k in range(3):
+        oracle.srand(100 + k)
+        frame, _ = oracle.render(nodes, s, 20, cam, 800, 600, use_bvh=(k != 1), want_samples=False)
+        assert sha(frame) == g["sha_frames"][k]
+        assert sha(oracle.accumulate(acc, k + 1, frame)) == g["sha_shown"][k]
+    assert sha(acc) == g["sha_accum"]
