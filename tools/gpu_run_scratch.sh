@@ -1,7 +1,13 @@
 #!/bin/bash
-# usage: gpurun --timeout 2400 -- bash tools/gpu_run_scratch.sh     (GPU test suite + default bench, outputs under gpurun_out/)
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
-tail -c 600 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'kernel_ms',d['roofline']['kernel_ms'], 'frac', d['roofline']['frac'], 'issue', d['roofline']['issue_bound']['frac'], 'launches', d['gpu_launches'])
+print(d['clocks']); print(d['cpu_baseline'])
+PY
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 | cut -c1-300
