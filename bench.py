@@ -65,7 +65,7 @@ def measured_peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  The timed region is a few milliseconds long, so the
-    sampler polls NVML from a thread every ~3 ms (nvidia-smi -lms cannot go below ~100 ms); it falls back to one
+    sampler polls NVML from a thread every ~2 ms (nvidia-smi -lms cannot go below ~100 ms); it falls back to one
     nvidia-smi query taken while a kernel loop is still in flight when NVML is unavailable."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
@@ -96,7 +96,7 @@ class ClockSampler:
                 self.samples.append((float(mhz), int(mask)))
             except Exception:
                 pass
-            time.sleep(0.003)
+            time.sleep(0.002)
 
     def start(self):
         if self.h is None:
@@ -117,7 +117,7 @@ class ClockSampler:
                 if mask & bit:
                     reasons.add(name)
         return {"sm_mhz": float(np.median([m for m, _ in self.samples])), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(reasons), "samples": len(self.samples), "how": "NVML polled every ~3 ms during the timed steps"}
+                "reasons": sorted(reasons), "samples": len(self.samples), "how": "NVML polled every ~2 ms during the timed steps"}
 
     def _smi_once(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -299,10 +299,10 @@ def run_b200(args):
     ids, fb_ptrs, fb_owned, assembly = None, None, None, None
     if dist_on:
         ok = 1
-        handles = [None, None]
+        handles = [None, None, None]
         try:
             if rank == 0:
-                fb_owned = [pkg.peer_alloc(world * n_local * 4, local) for _ in range(2)]
+                fb_owned = [pkg.peer_alloc(world * n_local * 4, local) for _ in range(2)] + [pkg.peer_alloc(8 * world, local)]
                 handles = [h for _, h in fb_owned]
         except Exception:
             ok = 0
@@ -320,10 +320,17 @@ def run_b200(args):
         dist.all_reduce(tok, op=dist.ReduceOp.MIN)
         if int(tok.item()) == 1:
             assembly = "peer"
-            flag = torch.zeros(1, dtype=torch.int64, device="cuda")
+            flags_ptr = fb_ptrs[2]           # world x uint64 on rank 0: slot r = last frame rank r has finished
+            if rank == 0:
+                for r in range(world):
+                    pkg.peer_signal(flags_ptr + 8 * r, 0, stream)
+                torch.cuda.synchronize()
+            dist.barrier()
         else:
             assembly = "all_gather"
             ids = [torch.empty((world, n_local), dtype=torch.int32, device="cuda") for _ in range(2)]
+
+    frame_no = [0]
 
     def run_steps(k_steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,23 +338,22 @@ def run_b200(args):
         e0.record()
         for k in range(k_steps):
             flush()
-            if dist_on:
+            if dist_on and assembly == "peer":
+                # the kernel stores the band into rank 0's frame; a one-thread kernel behind it stores "frame k done" into
+                # this rank's flag slot on rank 0.  No collective in the loop: the fence after the loop is the barrier.
+                frame_no[0] += 1
+                bvh.trace_primary_dev_prims(cam, W, H, y0, y1, hits_local.data_ptr(), fb_ptrs[k & 1] + rank * n_local * 4, stream)
+                pkg.peer_signal(flags_ptr + 8 * rank, frame_no[0], stream)
+            elif dist_on:
                 if gather_done[k & 1] is not None:
                     main_stream.wait_event(gather_done[k & 1])
-                if assembly == "peer":
-                    dst = fb_ptrs[k & 1] + rank * n_local * 4
-                else:
-                    buf = ids[k & 1]
-                    dst = buf[rank].data_ptr()
-                bvh.trace_primary_dev_prims(cam, W, H, y0, y1, hits_local.data_ptr(), dst, stream)
+                buf = ids[k & 1]
+                bvh.trace_primary_dev_prims(cam, W, H, y0, y1, hits_local.data_ptr(), buf[rank].data_ptr(), stream)
                 ek = torch.cuda.Event()
                 ek.record(main_stream)
                 with torch.cuda.stream(comm):
                     comm.wait_event(ek)
-                    if assembly == "peer":
-                        dist.all_reduce(flag)                  # every rank's kernel k is complete: frame k is whole on rank 0
-                    else:
-                        dist.all_gather_into_tensor(buf.view(world * n_local), buf[rank])
+                    dist.all_gather_into_tensor(buf.view(world * n_local), buf[rank])
                     gd = torch.cuda.Event()
                     gd.record(comm)
                     gather_done[k & 1] = gd
@@ -407,6 +413,8 @@ def run_b200(args):
         last = (args.steps - 1) & 1
         rebuilt = torch.empty((n_local, 8), dtype=torch.float32, device="cuda")
         ok = True
+        if assembly == "peer" and rank == 0:      # every rank has signalled the last frame through the peer mapping
+            ok = pkg.peer_read_flags(flags_ptr, world, stream) == [frame_no[0]] * world
         checks = range(1, world) if (assembly == "peer" and rank == 0) else ([] if assembly == "peer" else [(rank + 1) % world])
         for r in checks:
             ry0, ry1 = pkg.shard_rows(H, r, world)
@@ -536,8 +544,8 @@ def run_b200(args):
                    "timing": "one CUDA-event pair around the K steps on the launch stream, max over ranks",
                    "parallelism": f"rays sharded in {world} contiguous row band(s), BVH replicated" +
                                   ((", frame assembly fused into the trace kernel: every rank stores its band's 4-byte primitive ids straight "
-                                    "into rank 0's frame buffer over NVLink peer memory (CUDA IPC mapping), one 8-byte all_reduce per "
-                                    "frame as the completion barrier" if assembly == "peer" else
+                                    "into rank 0's frame buffer over NVLink peer memory (CUDA IPC mapping) and a completion flag behind it; "
+                                    "no collective inside the frame loop" if assembly == "peer" else
                                     ", NCCL all_gather of the frame's primitive-id buffer (4 B/pixel) on a side stream, double-buffered "
                                     "so gather k overlaps kernel k+1") if dist_on else "")},
         "clocks": clk,

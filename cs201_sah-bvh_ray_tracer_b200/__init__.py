@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "gpu_generate_primary_rays", "gpu_trace_brute_force", "gpu_trace_closest_hit_stats", "gpu_trace_primary_stats",
     "sahbvh_measure_peaks", "sahbvh_set_primary_mode", "gpu_trace_primary_dev_ids", "sahbvh_set_ray_mode",
     "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree", "gpu_bvh_download",
-    "sahbvh_peer_alloc", "sahbvh_peer_open", "sahbvh_peer_close", "sahbvh_peer_free",
+    "sahbvh_peer_alloc", "sahbvh_peer_open", "sahbvh_peer_close", "sahbvh_peer_free", "sahbvh_peer_signal", "sahbvh_peer_read_flags",
     "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
@@ -389,6 +389,16 @@ def peer_open(handle: bytes, device: int = -1) -> int:
     h = (C.c_ubyte * 64).from_buffer_copy(handle)
     _check(lib.sahbvh_peer_open(C.c_int(device), h, C.byref(p)), "sahbvh_peer_open")
     return int(p.value)
+
+
+def peer_signal(flag_ptr: int, value: int, stream: int = 0):
+    _check(lib.sahbvh_peer_signal(C.c_void_p(flag_ptr), C.c_uint64(value), C.c_void_p(stream)), "sahbvh_peer_signal")
+
+
+def peer_read_flags(flags_ptr: int, n: int, stream: int = 0) -> list[int]:
+    out = (C.c_uint64 * n)()
+    _check(lib.sahbvh_peer_read_flags(C.c_void_p(flags_ptr), C.c_int(n), out, C.c_void_p(stream)), "sahbvh_peer_read_flags")
+    return [int(v) for v in out]
 
 
 def peer_close(ptr: int, device: int = -1):

@@ -1484,6 +1484,38 @@ extern "C" int sahbvh_peer_open(int device, const sahbvh_ipc_handle *handle, voi
     return SAHBVH_OK;
 }
 
+/* "frame k of this rank is in place": ordered after the rank's trace kernel on the same stream, the store travels
+ * through the same peer mapping as the frame data (system-scope fence first) */
+__global__ void k_peer_signal(unsigned long long *flag, unsigned long long value)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(flag) = value;
+}
+
+extern "C" int sahbvh_peer_signal(void *d_flag, uint64_t value, void *stream)
+{
+    if (!d_flag) {
+        sahbvh_set_error("sahbvh_peer_signal: NULL flag");
+        return SAHBVH_E_ARG;
+    }
+    k_peer_signal<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long *)d_flag, (unsigned long long)value);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return SAHBVH_OK;
+}
+
+/* copies n 64-bit flags to the host (blocking on `stream`): the owner checks that every rank has signalled frame k */
+extern "C" int sahbvh_peer_read_flags(const void *d_flags, int n, uint64_t *out, void *stream)
+{
+    if (!d_flags || !out || n <= 0) {
+        sahbvh_set_error("sahbvh_peer_read_flags: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    CU_TRY(cudaMemcpyAsync(out, d_flags, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return SAHBVH_OK;
+}
+
 extern "C" int sahbvh_peer_close(int device, void *d_ptr)
 {
     if (!d_ptr) return SAHBVH_OK;

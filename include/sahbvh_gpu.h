@@ -139,6 +139,11 @@ int gpu_hits_from_prims_dev(gpu_bvh *bvh, const Camera *cam, int width, int heig
 typedef struct sahbvh_ipc_handle { unsigned char bytes[64]; } sahbvh_ipc_handle;
 int sahbvh_peer_alloc(int device, size_t bytes, void **d_ptr, sahbvh_ipc_handle *handle);
 int sahbvh_peer_open(int device, const sahbvh_ipc_handle *handle, void **d_ptr);
+/* Completion flags in the same peer memory: after its trace launch a rank stores the frame number into ITS 64-bit
+ * slot of a flag array owned by the root (a one-thread kernel ordered on the same stream, system-scope fence before
+ * the store); the root reads the slots when it wants to consume a frame.  No collective runs in the frame loop. */
+int sahbvh_peer_signal(void *d_flag, uint64_t value, void *stream);
+int sahbvh_peer_read_flags(const void *d_flags, int n, uint64_t *out, void *stream);
 int sahbvh_peer_close(int device, void *d_ptr);   /* for pointers from sahbvh_peer_open */
 int sahbvh_peer_free(int device, void *d_ptr);    /* for pointers from sahbvh_peer_alloc */
 /* Which kernel gpu_trace_primary* launches (process-wide; both give identical hit records):

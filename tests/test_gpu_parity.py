@@ -728,6 +728,8 @@ def test_peer_frame_buffer_between_processes(gpu, tmp_path):
     from common import ROOT
     n, W, H, y0, y1 = 20000, 1280, 720, 96, 480
     ptr, handle = gpu.peer_alloc(W * (y1 - y0) * 4)
+    fptr, fhandle = gpu.peer_alloc(8)
+    gpu.peer_signal(fptr, 0)
     script = f"""
 import sys
 sys.path.insert(0, {ROOT!r})
@@ -740,13 +742,17 @@ bvh = pkg.GpuBvh.build(s, {n}, 0, {n}, 0)
 dst = pkg.peer_open(bytes.fromhex({handle.hex()!r}))
 scratch = torch.empty(({W} * ({y1} - {y0}), 8), dtype=torch.float32, device="cuda")
 bvh.trace_primary_dev_prims(pkg.default_camera(), {W}, {H}, {y0}, {y1}, scratch.data_ptr(), dst, torch.cuda.current_stream().cuda_stream)
+flag = pkg.peer_open(bytes.fromhex({fhandle.hex()!r}))
+pkg.peer_signal(flag, 7, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 pkg.peer_close(dst)
+pkg.peer_close(flag)
 print("child ok")
 """
     try:
         out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and "child ok" in out.stdout, out.stderr[-2000:]
+        assert gpu.peer_read_flags(fptr, 1) == [7], "completion flag written through the peer mapping"
         gpu.srand(33)
         s = gpu.benchmark_scene(n)
         bvh = gpu.GpuBvh.build(s, n, 0, n, 0)
@@ -760,3 +766,4 @@ print("child ok")
         bvh.close()
     finally:
         gpu.peer_free(ptr)
+        gpu.peer_free(fptr)
