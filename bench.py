@@ -299,10 +299,11 @@ def run_b200(args):
     ids, fb_ptrs, fb_owned, assembly = None, None, None, None
     if dist_on:
         ok = 1
-        handles = [None, None, None]
+        handles = [None, None, None, None]
         try:
             if rank == 0:
-                fb_owned = [pkg.peer_alloc(world * n_local * 4, local) for _ in range(2)] + [pkg.peer_alloc(8 * world, local)]
+                fb_owned = ([pkg.peer_alloc(world * n_local * 4, local) for _ in range(2)] + [pkg.peer_alloc(8 * world, local)] +
+                            [pkg.peer_alloc(world * n_local * 4, local)])      # 2 id frames, flags, RGBA8 frame of the path loop
                 handles = [h for _, h in fb_owned]
         except Exception:
             ok = 0
@@ -383,12 +384,17 @@ def run_b200(args):
     render_multi = None
     if dist_on:
         # config-5 style frame assembly of the full path loop: every rank renders its band (trace_ray, MAX_DEPTH 5,
-        # 1 spp, counter-based draws) and the RGBA8 framebuffer (4 B/pixel) is all-gathered; same timing method
-        rgba = torch.empty((world, n_local), dtype=torch.int32, device="cuda")
+        # 1 spp, counter-based draws) and the RGBA8 framebuffer (4 B/pixel) is assembled on rank 0; same timing method
+        rgba = torch.empty((world, n_local), dtype=torch.int32, device="cuda") if assembly != "peer" else None
 
         def render_step():
-            bvh.render_frame_dev(cam, W, H, y0, y1, 5, 1, rgba[rank].data_ptr(), stream)
-            dist.all_gather_into_tensor(rgba.view(world * n_local), rgba[rank])
+            if assembly == "peer":      # k_resolve stores the band's RGBA8 pixels straight into rank 0's frame
+                frame_no[0] += 1
+                bvh.render_frame_dev(cam, W, H, y0, y1, 5, 1, fb_ptrs[3] + rank * n_local * 4, stream)
+                pkg.peer_signal(flags_ptr + 8 * rank, frame_no[0], stream)
+            else:
+                bvh.render_frame_dev(cam, W, H, y0, y1, 5, 1, rgba[rank].data_ptr(), stream)
+                dist.all_gather_into_tensor(rgba.view(world * n_local), rgba[rank])
 
         for _ in range(2):
             render_step()
@@ -402,7 +408,8 @@ def run_b200(args):
         fence()
         tr = torch.tensor([r0.elapsed_time(r1) / r_steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-        render_multi = {"workload": f"path loop (renderer.c:21-76), {W}x{H}, MAX_DEPTH 5, 1 spp, row bands + NCCL all_gather of the RGBA8 frame",
+        render_multi = {"workload": f"path loop (renderer.c:21-76), {W}x{H}, MAX_DEPTH 5, 1 spp, row bands, RGBA8 frame assembled on rank 0 " +
+                                    ("by the resolve kernels' peer stores" if assembly == "peer" else "by NCCL all_gather"),
                         "ms_per_frame": float(tr.item()), "value": total_rays / (float(tr.item()) * 1e-3) / 1e9, "unit": "Gpaths/s"}
     if dist_on:
         # untimed check of the assembled frame: the records rebuilt from the assembled ids of another rank's band must
