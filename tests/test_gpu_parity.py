@@ -767,3 +767,27 @@ print("child ok")
     finally:
         gpu.peer_free(ptr)
         gpu.peer_free(fptr)
+
+
+def test_c_example_reproduces_benchmark_counts(gpu, oracle, tmp_path):
+    """examples/benchmark_b200.c (benchmark.c's own loop on the C-ABI) prints the reference's two `intersections` counts."""
+    import re
+    import subprocess
+    from test_host_logic import _compile_example
+    exe = _compile_example(tmp_path)
+    out = subprocess.run([exe, "1", "5000", "10000", "5000"], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    found = [int(x) for x in re.findall(r"Intersections found: (\d+)", out.stdout)]
+    assert len(found) == 4
+    oracle.srand(1)
+    want = []
+    for n in (5000, 10000):
+        s = oracle.scene_benchmark(n)
+        nodes = oracle.build(s, 0, n - 1, 20)
+        rays_a, rays_b = oracle.rays_benchmark(10000), oracle.rays_benchmark(10000)
+        ha, _ = oracle.trace_brute(s, n, rays_a)
+        hb, _ = oracle.trace_bvh(nodes, s, n, rays_b)
+        want += [int((ha["prim"] >= 0).sum()), int((hb["prim"] >= 0).sum())]
+    assert found == want, (found, want)
+    rows = open(str(tmp_path / "benchmark_data.txt")).read().split()
+    assert rows[0] == "5000" and rows[3] == "10000" and len(rows) == 6
