@@ -197,6 +197,17 @@ int flat_bvh_from_tree(flat_bvh *f, const sah_tree *t, const Sphere *spheres, in
         float *q = f->spheres4 + (size_t)i * 4;
         q[0] = s->center.x; q[1] = s->center.y; q[2] = s->center.z; q[3] = s->radius;
         memcpy(&f->colors[i], &s->color, 4);
+        if (s->radius < 0.0f) {
+            /* bvh.c:26-35 builds an INVERTED box for a negative radius: the slab test (hit.c:49-82, min/max per axis)
+             * still treats the leaf as [c-|r|, c+|r|], but the ancestors' bounds no longer contain that interval, so the
+             * reference's recursion can cull a sphere whose own leaf test passes.  The leaf-only equivalence this library
+             * rests on needs containment; refuse loudly instead of returning different hits. */
+            sahbvh_set_error("flatten: sphere %d has a negative radius (%g): not supported, the reference's BVH result for it "
+                             "depends on ancestor boxes that do not contain it", i, (double)s->radius);
+            free(inner_id); free(depth);
+            flat_bvh_release(f);
+            return SAHBVH_E_ARG;
+        }
         float ar = fabsf(s->radius);
         if (ar > rmax) rmax = ar;
         const float *c = &s->center.x;

@@ -733,6 +733,7 @@ k_fl_spheres(const Sphere *__restrict__ all, int n_total, float *spheres4, uint3
     uint32_t c;
     memcpy(&c, &s.color, 4);
     colors[i] = c;
+    if (s.radius < 0.0f) st->bad_index = 1;                          /* the host flattener reports it (flatten.c) */
     const float ar = fabsf(s.radius);
     if (ar == ar) atomicMax(&st->rmax_bits, __float_as_uint(ar));   /* ar >= 0: bit order == value order */
     const float cc[3] = {s.center.x, s.center.y, s.center.z};
@@ -1219,6 +1220,7 @@ static int flatten_and_collapse(const sah_node *d_pre, int n_nodes, int tree_dep
     if (special_base > 0) FC_TRY(cudaMemcpy(parts->d_special, d_special_tmp, (size_t)special_base * 32, cudaMemcpyDeviceToDevice));
     else FC_TRY(cudaMemset(parts->d_special, 0, 32));
     FC_TRY(cudaMemcpy(&h_st, d_st, sizeof h_st, cudaMemcpyDeviceToHost));
+    if (h_st.bad_index) { rc = 1; goto out; }
     {
         gpu_bvh_info &info = parts->info;
         memset(&info, 0, sizeof info);

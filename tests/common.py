@@ -62,7 +62,9 @@ class HostEmul:
 
     def build(self, spheres, n_total, start, end, depth):
         h = self.lib.emul_build(_ptr(spheres), C.c_int(n_total), C.c_int(start), C.c_int(end), C.c_int(depth))
-        assert h
+        if not h:
+            self.lib.sahbvh_last_error.restype = C.c_char_p
+            raise RuntimeError(self.lib.sahbvh_last_error().decode())
         return h
 
     def from_pointers(self, spheres, n, root):

@@ -1,0 +1,118 @@
+"""Differential fuzzing against the oracle on small odd scenes: zero / tiny / huge radii, coincident and
+lattice centres, axis-parallel and unnormalised rays, origins inside spheres and far outside the scene.
+CPU: the traversal core compiled for the host (binary and 4-wide trees); GPU: every kernel through the C-ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from common import RAY_DT, SPHERE_DT, assert_hits_equal, same
+
+
+def odd_scene(rng, n):
+    s = np.zeros(n + 1, SPHERE_DT)
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        c = rng.uniform(-50, 50, size=(n, 3))
+    elif kind == 1:
+        c = np.round(rng.uniform(-20, 20, size=(n, 3)) / 5) * 5          # lattice: many coincident centres
+    elif kind == 2:
+        c = rng.normal(size=(n, 3)) * np.array([100.0, 1.0, 0.01])       # flat slab
+    else:
+        c = rng.uniform(-1, 1, size=(n, 3)) * 10.0 ** rng.integers(-3, 5)
+    s["c"][:n] = c.astype(np.float32)
+    # radii >= 0 only: a negative radius is refused at flatten time (test_negative_radius_is_refused below)
+    r = rng.choice([0.0, 1e-6, 0.3, 1.0, 2.5, 40.0], size=n, p=[0.05, 0.05, 0.3, 0.3, 0.2, 0.1])
+    s["r"][:n] = (r * rng.uniform(0.5, 1.5, size=n)).astype(np.float32)
+    s["rgba"][:n] = rng.integers(0, 256, size=(n, 4))
+    return s
+
+
+def odd_rays(rng, s, n, m):
+    rays = np.zeros(m, RAY_DT)
+    pick = rng.integers(0, n, m)
+    o = s["c"][pick].astype(np.float64) + rng.normal(size=(m, 3)) * rng.choice([0.0, 0.1, 3.0, 500.0], size=(m, 1))
+    d = rng.normal(size=(m, 3)) * rng.choice([1e-3, 1.0, 50.0], size=(m, 1))
+    aim = rng.random(m) < 0.4                                              # aim a share of the rays at sphere centres
+    tgt = s["c"][rng.integers(0, n, m)].astype(np.float64)
+    d[aim] = (tgt - o)[aim]
+    axis = rng.random(m) < 0.15                                            # axis-parallel / tiny components
+    d[axis, rng.integers(0, 3, axis.sum())] = rng.choice([0.0, -0.0, 1e-12, 1e-35, 1e-41], axis.sum())
+    rays["o"] = o.astype(np.float32)
+    rays["d"] = d.astype(np.float32)
+    return rays
+
+
+CASES = [(seed, n) for seed, n in ((1, 2), (2, 17), (3, 64), (4, 300), (5, 1500), (6, 5000), (7, 9000), (8, 40))]
+# SAHBVH_FUZZ_EXTRA=K adds K more seeded cases (development soak runs; the default set keeps the suite short)
+for _k in range(int(os.environ.get("SAHBVH_FUZZ_EXTRA", "0"))):
+    CASES.append((100 + _k, int(np.random.default_rng(100 + _k).choice([1, 3, 9, 33, 120, 700, 2500, 7000]))))
+
+
+@pytest.mark.parametrize("seed,n", CASES)
+def test_fuzz_host_core(oracle, emul, seed, n):
+    rng = np.random.default_rng(seed)
+    s = odd_scene(rng, n)
+    so = s.copy()
+    depth0 = int(rng.choice([0, 0, 20, 36]))
+    nodes = oracle.build(so, 0, n, depth0)
+    h = emul.build(s, n, 0, n, depth0)
+    assert same(s, so)
+    rays = odd_rays(rng, so, n, 3000)
+    want, _ = oracle.trace_bvh(nodes, so, n, rays)
+    got, _ = emul.trace(h, rays)
+    assert_hits_equal(got, want, f"fuzz seed {seed} n {n} depth0 {depth0}")
+    emul.free(h)
+
+
+def test_negative_radius_is_refused(emul):
+    """bvh.c:26-35 turns a negative radius into an inverted box that its ancestors' bounds do not contain, so the
+    reference's recursion and a leaf-only traversal can disagree (found by this fuzzer): the flattener says so."""
+    rng = np.random.default_rng(11)
+    s = odd_scene(rng, 50)
+    s["r"][7] = -0.5
+    with pytest.raises(Exception, match="negative radius"):
+        emul.build(s, 50, 0, 50, 0)
+
+
+@pytest.mark.gpu
+def test_negative_radius_is_refused_gpu(pkg):
+    rng = np.random.default_rng(11)
+    for n in (50, 6000):                       # host and device build paths
+        s = odd_scene(rng, n)
+        s["r"][n // 2] = -0.5
+        with pytest.raises(pkg.SahBvhError, match="negative radius"):
+            pkg.GpuBvh.build(s, n, 0, n, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n", CASES)
+def test_fuzz_gpu(pkg, oracle, seed, n):
+    gpu = pkg
+    rng = np.random.default_rng(seed)
+    s = odd_scene(rng, n)
+    so = s.copy()
+    depth0 = int(rng.choice([0, 0, 20, 36]))
+    nodes = oracle.build(so, 0, n, depth0)
+    rays = odd_rays(rng, so, n, 20000)
+    want, _ = oracle.trace_bvh(nodes, so, n, rays)
+    cam = gpu.default_camera()
+    cam["position"] = tuple(float(v) for v in (so["c"][:n].mean(axis=0) + np.array([0.0, 0.0, 3.0 * (np.abs(so["c"][:n]).max() + 1)])))
+    prim_want, _ = oracle.trace_bvh(nodes, so, n, oracle.primary_rays(cam, 320, 200))
+    try:
+        for build_mode in (gpu.BUILD_HOST, gpu.BUILD_DEVICE):
+            gpu.set_build_mode(build_mode)
+            sb = s.copy()
+            bvh = gpu.GpuBvh.build(sb, n, 0, n, depth0)
+            assert same(sb, so)
+            for mode in (gpu.RAYS_WIDE, gpu.RAYS_COOP, gpu.RAYS_ONE_SHOT):
+                gpu.set_ray_mode(mode)
+                assert_hits_equal(bvh.trace_closest_hit(rays), want, f"fuzz seed {seed} n {n} ray mode {mode} build {build_mode}")
+            for pmode in (gpu.PRIMARY_PACKET, gpu.PRIMARY_PER_RAY):
+                gpu.set_primary_mode(pmode)
+                assert_hits_equal(bvh.trace_primary(cam, 320, 200), prim_want, f"fuzz seed {seed} n {n} primary mode {pmode}")
+            bvh.close()
+    finally:
+        gpu.set_build_mode(gpu.BUILD_DEVICE)
+        gpu.set_ray_mode(gpu.RAYS_WIDE)
+        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
