@@ -490,6 +490,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
         float min_len = sqrtf(lmin_a);
         const float cull_abs = (min_len > 0.0f) ? (2.0f * sc.r_max) / min_len : INFINITY;
         float pkt_best_s = INFINITY;
+        const bool simple = sah_frustum_simple(FX, FY, FZ);   /* warp-uniform */
 
         int top = 1;
         if (lane == 0) stack[0] = 0;
@@ -504,27 +505,28 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
             top -= npop;
             if (COUNT && lane == 0) cnt.inner += (unsigned long long)npop;
             bool pass = false;
-            float tn = INFINITY, lox = 0, loy = 0, loz = 0, hix = 0, hiy = 0, hiz = 0;
+            float tn = INFINITY;
             int32_t ref = SAH_REF_NONE;
             if (active) {
                 /* 128-byte 4-wide node (wide.c, full-precision twin): lane (j, c) tests child c of popped node j */
                 const float4 *rec = reinterpret_cast<const float4 *>(nodes + (size_t)nd * 32 + c * 8);
-                float4 c0 = __ldg(rec), c1 = __ldg(rec + 1);
-                lox = c0.x; loy = c0.y; loz = c0.z; hix = c0.w; hiy = c1.x; hiz = c1.y;
+                const float4 c0 = __ldg(rec), c1 = __ldg(rec + 1);
                 ref = __float_as_int(c1.z);
-                pass = ref != SAH_REF_NONE && sah_frustum_box(FX, FY, FZ, lox, loy, loz, hix, hiy, hiz, pkt_best_s, tn);
+                /* an absent child (SAH_REF_NONE) carries an inverted box: it fails the test unless every axis is ignored */
+                pass = simple ? sah_frustum_box_simple(FX, FY, FZ, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, pkt_best_s, tn)
+                              : sah_frustum_box(FX, FY, FZ, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, pkt_best_s, tn);
+                pass = pass && ref != SAH_REF_NONE;
             }
             const bool is_leaf = ref < 0;
             const bool push = pass && !is_leaf;
             const bool cand = pass && is_leaf && (uint32_t)(~ref) < (uint32_t)sc.n_spheres;
             /* stack order: children of deeper stack entries first, of the top entry last; within a node far first,
              * near last (rank among the four siblings by packet entry distance, ties by slot) */
+            /* tn >= 0 or +inf, so its bit pattern orders like the value; the two low bits carry the slot */
+            const uint32_t key = (__float_as_uint(tn) & 0x7ffffffcu) | (uint32_t)c;
             int rank = 0;
 #pragma unroll
-            for (int x = 1; x < 4; x++) {
-                const float to = __shfl_xor_sync(full, tn, x);
-                rank += (to < tn || (to == tn && (c ^ x) < c)) ? 1 : 0;
-            }
+            for (int x = 1; x < 4; x++) rank += (__shfl_xor_sync(full, key, x) < key) ? 1 : 0;
             const int order = (7 - j) * 4 + (3 - rank);
             unsigned ord_mask = __reduce_or_sync(full, push ? (1u << order) : 0u);
             if (push) stack[top + __popc(ord_mask & ((1u << order) - 1u))] = ref;
@@ -559,8 +561,10 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                     }
                 }
                 if (__any_sync(full, needk != 0)) {
-                    const float blx = __shfl_sync(full, lox, src), bly = __shfl_sync(full, loy, src), blz = __shfl_sync(full, loz, src);
-                    const float bhx = __shfl_sync(full, hix, src), bhy = __shfl_sync(full, hiy, src), bhz = __shfl_sync(full, hiz, src);
+                    /* the candidate's own box, re-read from its node (an L1 hit, same address for every lane) */
+                    const float4 *brec = reinterpret_cast<const float4 *>(nodes + (size_t)__shfl_sync(full, nd, src) * 32 + (src & 3) * 8);
+                    const float4 b0 = __ldg(brec), b1 = __ldg(brec + 1);
+                    const float blx = b0.x, bly = b0.y, blz = b0.z, bhx = b0.w, bhy = b1.x, bhz = b1.y;
 #pragma unroll kPktUnroll
                     for (int k = 0; k < PKT_K; k++) {
                         if (needk & (1u << k)) {

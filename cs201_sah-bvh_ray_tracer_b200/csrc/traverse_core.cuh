@@ -715,4 +715,29 @@ SAH_HD bool sah_frustum_box(const SahFrustumAxis &X, const SahFrustumAxis &Y, co
     return tn <= F_FMA(tf, SAH_REL_PKT, 1e-37f) && tn <= best_s;
 }
 
+/* sah_frustum_box for a tile whose three axes are all in mode 0 or 1 (the common case: no direction interval
+ * straddles zero).  Same arithmetic as sah_frustum_axis for those modes, without its per-axis mode branches. */
+SAH_HD bool sah_frustum_simple(const SahFrustumAxis &X, const SahFrustumAxis &Y, const SahFrustumAxis &Z) {
+    return X.mode <= 1 && Y.mode <= 1 && Z.mode <= 1;
+}
+
+SAH_HD void sah_frustum_axis_simple(const SahFrustumAxis &A, float lo, float hi, float &LB, float &UB) {
+    const bool pos = A.mode == 0;
+    const float qn = F_SUB(pos ? lo : hi, A.o), qf = F_SUB(pos ? hi : lo, A.o);
+    LB = fminf(F_MUL(qn, A.ia), F_MUL(qn, A.ib));
+    UB = fmaxf(F_MUL(qf, A.ia), F_MUL(qf, A.ib));
+}
+
+SAH_HD bool sah_frustum_box_simple(const SahFrustumAxis &X, const SahFrustumAxis &Y, const SahFrustumAxis &Z,
+                                   float lox, float loy, float loz, float hix, float hiy, float hiz, float best_s, float &tnear) {
+    float lbx, ubx, lby, uby, lbz, ubz;
+    sah_frustum_axis_simple(X, lox, hix, lbx, ubx);
+    sah_frustum_axis_simple(Y, loy, hiy, lby, uby);
+    sah_frustum_axis_simple(Z, loz, hiz, lbz, ubz);
+    float tn = fmaxf(fmaxf(fmaxf(lbx, lby), lbz), 0.0f);
+    float tf = fminf(fminf(ubx, uby), ubz);
+    tnear = tn;
+    return tn <= F_FMA(tf, SAH_REL_PKT, 1e-37f) && tn <= best_s;
+}
+
 #endif /* SAHBVH_TRAVERSE_CORE_CUH */
