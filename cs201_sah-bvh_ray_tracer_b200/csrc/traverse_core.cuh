@@ -521,13 +521,16 @@ SAH_UNROLL
         if (over >= 0) return self;
     }
     if (COUNT) cnt->inner++;
-    /* inner children, nearest first; ties by slot */
+    /* inner children, nearest first: tn >= 0, so its bit pattern orders like its value (the order among equal
+     * entry distances only affects the visiting order, never the result) */
     uint32_t k0, k1, k2, k3;
     {
         uint32_t k[4];
 SAH_UNROLL
-        for (int c = 0; c < 4; c++)
-            k[c] = (hit[c] && ref[c] >= 0) ? ((sah_f2u(tn[c]) & 0x7ffffffcu) + (uint32_t)c) : SAH_KEY_NONE;
+        for (int c = 0; c < 4; c++) {
+            const bool inner_hit = hit[c] & (ref[c] >= 0);
+            k[c] = inner_hit ? sah_f2u(tn[c]) : SAH_KEY_NONE;
+        }
         k0 = k[0]; k1 = k[1]; k2 = k[2]; k3 = k[3];
     }
     int32_t r0 = ref[0], r1 = ref[1], r2 = ref[2], r3 = ref[3];
