@@ -418,6 +418,9 @@ static constexpr int kPktUnroll = PKT_UNROLL;
 #ifndef PKT_MIN_BLOCKS
 #define PKT_MIN_BLOCKS 8
 #endif
+#ifndef PKT_BLOCK_2X2
+#define PKT_BLOCK_2X2 (PKT_WARPS == 4)
+#endif
 
 __device__ __forceinline__ float warp_min(float v)
 {
@@ -448,12 +451,20 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (width + 15) >> 4, tiles_y = (y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H;
-    const unsigned tile = blockIdx.x * PKT_WARPS + warp;   /* < 2^31: the launch rejects larger frames */
     SahCounters cnt = {0, 0, 0, 0};
     unsigned long long hits = 0;
+#if PKT_BLOCK_2X2
+    /* the block's 4 warps own a 2x2 group of tiles (32x16 pixels): their frusta overlap more than those of a 4x1 strip */
+    const unsigned groups_x = (unsigned)(tiles_x + 1) >> 1;
+    const int ty = (int)(blockIdx.x / groups_x) * 2 + (warp >> 1), tx = (int)(blockIdx.x % groups_x) * 2 + (warp & 1);
+    if (tx < tiles_x && ty < tiles_y) {
+        int32_t *stack = s_stack[warp];
+#else
+    const unsigned tile = blockIdx.x * PKT_WARPS + warp;   /* < 2^31: the launch rejects larger frames */
     if (tile < (unsigned)tiles_x * (unsigned)tiles_y) {
         int32_t *stack = s_stack[warp];
         const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile - (unsigned)ty * (unsigned)tiles_x);
+#endif
         /* ---- this lane's 4 rays: pixel (tx*16 + (k&1)*8 + lane%8, y0 + ty*8 + (k>>1)*4 + lane/8) ---- */
         const int px0 = tx * 16 + (lane & 7), py0 = y0 + ty * PKT_TILE_H + (lane >> 3);
         unsigned valid = 0;
@@ -1125,6 +1136,7 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
             return SAHBVH_E_ARG;
         }
         unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
+        if (PKT_BLOCK_2X2) grid = (unsigned)(((width + 31) / 32) * ((y1 - y0 + 2 * PKT_TILE_H - 1) / (2 * PKT_TILE_H)));
         if (count)
             k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                          out, ids, ids_prim_only, b->d_counters);
