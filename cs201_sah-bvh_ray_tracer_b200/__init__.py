@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "gpu_benchmark_no_bvh", "gpu_benchmark_with_bvh", "sahbvh_set_build_mode", "sahbvh_build_tree", "gpu_bvh_download",
     "sahbvh_peer_alloc", "sahbvh_peer_open", "sahbvh_peer_close", "sahbvh_peer_free", "sahbvh_peer_signal", "sahbvh_peer_read_flags",
     "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
+    "sahbvh_host_alloc", "sahbvh_host_free", "sahbvh_host_pin", "sahbvh_host_unpin",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
@@ -374,6 +375,15 @@ class GpuBvh:
         _check(lib.gpu_trace_primary_stats(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
                                            C.c_void_p(d_out), C.byref(st)), "gpu_trace_primary_stats")
         return st.as_dict()
+
+
+def host_pin(arr) -> None:
+    """sahbvh_host_pin: page-lock a numpy array in place so the host-pointer entry points copy at PCIe speed."""
+    _check(lib.sahbvh_host_pin(C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes)), "sahbvh_host_pin")
+
+
+def host_unpin(arr) -> None:
+    _check(lib.sahbvh_host_unpin(C.c_void_p(arr.ctypes.data)), "sahbvh_host_unpin")
 
 
 def peer_alloc(nbytes: int, device: int = -1) -> tuple[int, bytes]:

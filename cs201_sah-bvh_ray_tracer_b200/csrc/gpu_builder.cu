@@ -67,11 +67,18 @@ struct GbBins {
 struct GbSmall { int32_t node, start, end, depth; };
 struct GbCounters { int32_t nodes, next_work, small, overflow, max_depth, pad[3]; };
 
+/* error text for sahbvh_last_error(); clears the runtime's non-sticky last-error slot (see gpu_handle.cuh) */
+static inline const char *cu_errstr(cudaError_t e)
+{
+    (void)cudaGetLastError();
+    return cudaGetErrorString(e);
+}
+
 #define GB_TRY(expr)                                                                               \
     do {                                                                                           \
         cudaError_t _e = (expr);                                                                   \
         if (_e != cudaSuccess) {                                                                   \
-            sahbvh_set_error("gpu builder: %s failed: %s", #expr, cudaGetErrorString(_e));        \
+            sahbvh_set_error("gpu builder: %s failed: %s", #expr, cu_errstr(_e));        \
             rc = SAHBVH_E_CUDA;                                                                    \
             goto done;                                                                             \
         }                                                                                          \
@@ -1067,7 +1074,7 @@ static int gb_build(sah_tree *t, Sphere *spheres, int n_total, int start, int en
         if (start != 0 || end != n_total) { /* indices are global: the kernels need the whole array */
             GB_TRY(cudaMalloc((void **)&d_all_owned, (size_t)n_total * sizeof(Sphere)));
             cudaError_t e = cudaMemcpy(d_all_owned, spheres, (size_t)n_total * sizeof(Sphere), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) { cudaFree(d_all_owned); sahbvh_set_error("gpu builder: %s", cudaGetErrorString(e)); rc = SAHBVH_E_CUDA; goto done; }
+            if (e != cudaSuccess) { cudaFree(d_all_owned); sahbvh_set_error("gpu builder: %s", cu_errstr(e)); rc = SAHBVH_E_CUDA; goto done; }
             d_all = d_all_owned;
         }
         rc = flatten_and_collapse(d_pre, h_ctr.nodes, h_ctr.max_depth, d_all, n_total, parts, timing);
@@ -1119,7 +1126,7 @@ extern "C" int gpu_build_parts(Sphere *spheres, int n_total, int start, int end,
     do {                                                                                           \
         cudaError_t _e = (expr);                                                                   \
         if (_e != cudaSuccess) {                                                                   \
-            sahbvh_set_error("gpu flatten: %s failed: %s", #expr, cudaGetErrorString(_e));        \
+            sahbvh_set_error("gpu flatten: %s failed: %s", #expr, cu_errstr(_e));        \
             rc = SAHBVH_E_CUDA;                                                                    \
             goto out;                                                                              \
         }                                                                                          \

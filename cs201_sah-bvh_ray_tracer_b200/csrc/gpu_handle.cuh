@@ -52,11 +52,19 @@ struct DeviceGuard {
 
 extern std::atomic<unsigned long long> g_launches;
 
+/* text of a runtime error that is being reported through sahbvh_last_error(); also clears the runtime's
+ * (non-sticky) last-error slot so that the next launch check does not report the same failure again */
+static inline const char *cu_errstr(cudaError_t e)
+{
+    (void)cudaGetLastError();
+    return cudaGetErrorString(e);
+}
+
 #define CU_TRY(expr)                                                                              \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \
         if (_e != cudaSuccess) {                                                                  \
-            sahbvh_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            sahbvh_set_error("%s failed: %s (%s:%d)", #expr, cu_errstr(_e), __FILE__, __LINE__); \
             return SAHBVH_E_CUDA;                                                                 \
         }                                                                                         \
     } while (0)

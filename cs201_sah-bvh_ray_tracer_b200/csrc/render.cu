@@ -241,7 +241,7 @@ extern "C" int gpu_render_frame_dev(gpu_bvh *b, const Camera *cam, int width, in
             k_fill<<<(unsigned)((n_pixels + RN_THREADS - 1) / RN_THREADS), RN_THREADS, 0, st>>>((uint32_t *)d_rgba, n_pixels, 0xff000000u);
             g_launches++;
             cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) { sahbvh_set_error("gpu_render_frame: %s", cudaGetErrorString(e)); rc = SAHBVH_E_CUDA; }
+            if (e != cudaSuccess) { sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e)); rc = SAHBVH_E_CUDA; }
             break;
         }
         RenderBufs rb;
@@ -269,7 +269,7 @@ extern "C" int gpu_render_frame_dev(gpu_bvh *b, const Camera *cam, int width, in
             if (e == cudaSuccess) e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaMemcpyAsync(&h_count, rb.count, sizeof h_count, cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { sahbvh_set_error("gpu_render_frame: %s", cudaGetErrorString(e)); rc = SAHBVH_E_CUDA; break; }
+            if (e != cudaSuccess) { sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e)); rc = SAHBVH_E_CUDA; break; }
             cur ^= 1;
             n_rays = (long long)h_count;
             if (n_rays > 0 && k + 1 < max_depth) {
@@ -282,7 +282,7 @@ extern "C" int gpu_render_frame_dev(gpu_bvh *b, const Camera *cam, int width, in
                                                                                                max_depth, (uint32_t *)d_rgba);
         g_launches++;
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { sahbvh_set_error("gpu_render_frame: %s", cudaGetErrorString(e)); rc = SAHBVH_E_CUDA; }
+        if (e != cudaSuccess) { sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e)); rc = SAHBVH_E_CUDA; }
     } while (0);
     if (prev >= 0 && prev != b->device) cudaSetDevice(prev);
     return rc;
@@ -309,7 +309,7 @@ extern "C" int gpu_render_frame(gpu_bvh *b, const Camera *cam, int width, int he
             e = cudaMemcpyAsync(d_samples, samples, (size_t)n_pixels * (size_t)max_depth * sizeof(Vec3), cudaMemcpyHostToDevice, b->streams[0]);
     }
     if (e != cudaSuccess) {
-        sahbvh_set_error("gpu_render_frame: %s", cudaGetErrorString(e));
+        sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e));
         rc = SAHBVH_E_CUDA;
     }
     if (rc == SAHBVH_OK) rc = gpu_render_frame_dev(b, cam, width, height, y0, y1, max_depth, seed, d_samples, d_rgba, b->streams[0]);
@@ -317,7 +317,7 @@ extern "C" int gpu_render_frame(gpu_bvh *b, const Camera *cam, int width, int he
         e = cudaMemcpyAsync(rgba_out, d_rgba, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost, b->streams[0]);
         if (e == cudaSuccess) e = cudaStreamSynchronize(b->streams[0]);
         if (e != cudaSuccess) {
-            sahbvh_set_error("gpu_render_frame: %s", cudaGetErrorString(e));
+            sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e));
             rc = SAHBVH_E_CUDA;
         }
     }
@@ -365,7 +365,7 @@ extern "C" int gpu_accumulate(float *accum, int frames, const uint8_t *rgba, int
     if (e == cudaSuccess && rc == SAHBVH_OK) e = cudaMemcpy(avg_rgba, d_avg, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost);
     cudaFree(d_acc); cudaFree(d_rgba); cudaFree(d_avg);
     if (e != cudaSuccess) {
-        sahbvh_set_error("gpu_accumulate: %s", cudaGetErrorString(e));
+        sahbvh_set_error("gpu_accumulate: %s", cu_errstr(e));
         return SAHBVH_E_CUDA;
     }
     return rc;

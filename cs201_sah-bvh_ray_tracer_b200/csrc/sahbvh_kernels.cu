@@ -785,7 +785,7 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
         sahbvh_set_error("no usable CUDA device (%s); this library has no CPU traversal path",
-                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+                         e == cudaSuccess ? "device count is 0" : cu_errstr(e));
         cudaGetLastError();
         return SAHBVH_E_CUDA;
     }
@@ -838,7 +838,7 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
     } while (0);
     wide_bvh_release(&wb);
     if (err != cudaSuccess) {
-        sahbvh_set_error("gpu_bvh upload failed: %s", cudaGetErrorString(err));
+        sahbvh_set_error("gpu_bvh upload failed: %s", cu_errstr(err));
         gpu_bvh_free(b);
         return SAHBVH_E_CUDA;
     }
@@ -874,7 +874,7 @@ static int gpu_bvh_from_parts(gpu_bvh_parts *p, int device, gpu_bvh **out)
         if ((err = cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) break;
     } while (0);
     if (err != cudaSuccess) {
-        sahbvh_set_error("gpu_bvh set-up failed: %s", cudaGetErrorString(err));
+        sahbvh_set_error("gpu_bvh set-up failed: %s", cu_errstr(err));
         gpu_bvh_free(b);
         return SAHBVH_E_CUDA;
     }
@@ -1362,7 +1362,7 @@ extern "C" int gpu_generate_primary_rays(const Camera *cam, int width, int heigh
     if (e == cudaSuccess) e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) {
-        sahbvh_set_error("gpu_generate_primary_rays: %s", cudaGetErrorString(e));
+        sahbvh_set_error("gpu_generate_primary_rays: %s", cu_errstr(e));
         return SAHBVH_E_CUDA;
     }
     return SAHBVH_OK;
@@ -1463,6 +1463,51 @@ extern "C" int gpu_benchmark_with_bvh(gpu_bvh *b, const Ray *rays, int64_t n, in
 /* ------------------------------------------------------------------------------------------ */
 /* peer framebuffer: the trace kernel of every rank stores its band straight into ONE GPU's frame  */
 /* ------------------------------------------------------------------------------------------ */
+/* page-locked host memory for callers without the CUDA headers (see sahbvh_gpu.h) */
+static int host_mem_ready(const char *who, bool ok_args)
+{
+    if (!ok_args) {
+        sahbvh_set_error("%s: bad arguments", who);
+        return SAHBVH_E_ARG;
+    }
+    if (sahbvh_device_count() == 0) {
+        sahbvh_set_error("no usable CUDA device");
+        return SAHBVH_E_CUDA;
+    }
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_host_alloc(size_t bytes, void **ptr)
+{
+    if (ptr) *ptr = nullptr;
+    int rc = host_mem_ready("sahbvh_host_alloc", ptr != nullptr && bytes > 0);
+    if (rc != SAHBVH_OK) return rc;
+    CU_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_host_free(void *ptr)
+{
+    if (!ptr) return SAHBVH_OK;
+    CU_TRY(cudaFreeHost(ptr));
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_host_pin(void *ptr, size_t bytes)
+{
+    int rc = host_mem_ready("sahbvh_host_pin", ptr != nullptr && bytes > 0);
+    if (rc != SAHBVH_OK) return rc;
+    CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return SAHBVH_OK;
+}
+
+extern "C" int sahbvh_host_unpin(void *ptr)
+{
+    if (!ptr) return SAHBVH_OK;
+    CU_TRY(cudaHostUnregister(ptr));
+    return SAHBVH_OK;
+}
+
 static_assert(sizeof(sahbvh_ipc_handle) == sizeof(cudaIpcMemHandle_t), "IPC handle size");
 
 extern "C" int sahbvh_peer_alloc(int device, size_t bytes, void **d_ptr, sahbvh_ipc_handle *handle)
@@ -1484,7 +1529,7 @@ extern "C" int sahbvh_peer_alloc(int device, size_t bytes, void **d_ptr, sahbvh_
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {
         cudaFree(p);
-        sahbvh_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        sahbvh_set_error("cudaIpcGetMemHandle failed: %s", cu_errstr(e));
         return SAHBVH_E_CUDA;
     }
     memcpy(handle, &h, sizeof h);

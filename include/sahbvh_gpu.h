@@ -146,6 +146,15 @@ int sahbvh_peer_signal(void *d_flag, uint64_t value, void *stream);
 int sahbvh_peer_read_flags(const void *d_flags, int n, uint64_t *out, void *stream);
 int sahbvh_peer_close(int device, void *d_ptr);   /* for pointers from sahbvh_peer_open */
 int sahbvh_peer_free(int device, void *d_ptr);    /* for pointers from sahbvh_peer_alloc */
+/* Page-locked host buffers for the host-pointer entry points (gpu_trace_closest_hit, gpu_trace_primary, ...):
+ * their copies run at PCIe speed (~54 GB/s measured) only when the caller's ray / hit arrays are page-locked;
+ * with malloc'ed memory the driver stages every copy through its own bounce buffer.  A C caller without the CUDA
+ * headers gets page-locked memory here: sahbvh_host_alloc/free for new buffers, sahbvh_host_pin/unpin around an
+ * existing array (e.g. the static frame buffer of main.c:356-366) for as long as it is passed to the library. */
+int sahbvh_host_alloc(size_t bytes, void **ptr);
+int sahbvh_host_free(void *ptr);
+int sahbvh_host_pin(void *ptr, size_t bytes);
+int sahbvh_host_unpin(void *ptr);
 /* Which kernel gpu_trace_primary* launches (process-wide; both give identical hit records):
  *   SAHBVH_PRIMARY_PACKET  (default) one warp per 16x8 pixel tile, interior culling once per tile
  *   SAHBVH_PRIMARY_PER_RAY one thread per pixel, per-ray stack traversal (the ray-buffer kernel's core) */

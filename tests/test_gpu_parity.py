@@ -149,6 +149,32 @@ def test_100k_bounce_rays(gpu, oracle, golden, scene100k):
     assert_hits_equal(bh[:4096], vec["bench_100000_bounce__hits"], "bounce")
 
 
+def test_host_pinning_helpers(gpu, scene100k):
+    """sahbvh_host_pin / sahbvh_host_unpin: the same records arrive in a page-locked caller array, and the
+    second unpin of the same array is reported as an error instead of being ignored."""
+    bvh, s, rays, _ = scene100k
+    sub = np.ascontiguousarray(rays[:200000])
+    want = bvh.trace_closest_hit(sub)
+    out = np.zeros(len(sub), HIT_DT)
+    gpu.host_pin(sub)
+    gpu.host_pin(out)
+    try:
+        got = bvh.trace_closest_hit(sub, out)
+        assert_hits_equal(got, want, "pinned host arrays")
+        cam = gpu.default_camera()
+        frame = np.zeros(640 * 360, HIT_DT)
+        gpu.host_pin(frame)
+        try:
+            assert_hits_equal(bvh.trace_primary(cam, 640, 360, out=frame), bvh.trace_primary(cam, 640, 360), "pinned frame")
+        finally:
+            gpu.host_unpin(frame)
+    finally:
+        gpu.host_unpin(out)
+        gpu.host_unpin(sub)
+    with pytest.raises(gpu.SahBvhError):
+        gpu.host_unpin(out)
+
+
 def test_100k_bvh_vs_brute_force_on_gpu(gpu, scene100k):
     bvh, s, rays, _ = scene100k
     sub = rays[:8192]
