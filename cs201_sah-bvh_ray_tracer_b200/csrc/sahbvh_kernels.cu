@@ -441,8 +441,8 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
 {
     /* The traversal loop is a chain of dependent node fetches, so it needs resident warps more than registers:
      * the per-ray state (direction, d.d, best t, best index of the lane's 4 rays) lives in shared memory -- it is
-     * only touched when a candidate leaf is tested (about 5 times per tile) -- which leaves ~56 registers per
-     * thread and 10 CTAs (40 warps) per SM instead of 5. */
+     * only touched when a candidate leaf is tested (about 5 times per tile) -- which leaves 62 registers per
+     * thread and 8 CTAs (32 warps) per SM instead of 5. */
     __shared__ int32_t s_stack[PKT_WARPS][PKT_STACK];
     __shared__ float s_ray[PKT_WARPS][PKT_K][4][32];   /* dx, dy, dz, d.d */
     __shared__ float s_bt[PKT_WARPS][PKT_K][32];

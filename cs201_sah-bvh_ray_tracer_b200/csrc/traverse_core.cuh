@@ -631,13 +631,7 @@ SAH_HD void sah_primary_dir_uv(const SahCamera &c, float u, float v, float &dx, 
 
 /* main.c:362-365 + ray.c:26-31 for pixel (x,y): direction only (origin = position) */
 SAH_HD void sah_primary_dir(const SahCamera &c, int x, int y, float &dx, float &dy, float &dz) {
-    float u = F_MUL(F_SUB(F_DIV((float)x, c.fw), 0.5f), c.aspect);
-    float v = -F_SUB(F_DIV((float)y, c.fh), 0.5f);
-    float ax = F_ADD(c.fx, F_MUL(c.hx, u)), ay = F_ADD(c.fy, F_MUL(c.hy, u)), az = F_ADD(c.fz, F_MUL(c.hz, u));
-    ax = F_ADD(ax, F_MUL(c.vx, v)); ay = F_ADD(ay, F_MUL(c.vy, v)); az = F_ADD(az, F_MUL(c.vz, v));
-    float len = F_SQRT(F_ADD(F_ADD(F_MUL(ax, ax), F_MUL(ay, ay)), F_MUL(az, az)));
-    if (len != 0.0f) { dx = F_DIV(ax, len); dy = F_DIV(ay, len); dz = F_DIV(az, len); }
-    else { dx = 0.0f; dy = 0.0f; dz = 0.0f; }
+    sah_primary_dir_uv(c, sah_pixel_u(c, x), sah_pixel_v(c, y), dx, dy, dz);
 }
 
 /* ---------------------------------------------------------------------------------------------
