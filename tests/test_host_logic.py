@@ -352,3 +352,16 @@ def test_c_example_compiles_and_links(pkg, tmp_path):
     if pkg.device_count() == 0:     # no GPU here: the binary must refuse loudly instead of falling back to a CPU path
         out = subprocess.run([exe, "1", "5000", "5000", "5000"], capture_output=True, text=True, cwd=str(tmp_path))
         assert out.returncode != 0 and "no usable CUDA device" in out.stderr
+
+
+def test_public_headers_are_strict_c99_and_cxx17(tmp_path):
+    """include/*.h are the drop-in boundary: they must be usable from the reference's plain C and from C++ hosts."""
+    import subprocess
+    src = '#include "sahbvh_gpu.h"\n#include "sahbvh_ref_api.h"\nint main(void) { return 0; }\n'
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "hdr.c"
+    c.write_text(src)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(c)])
+    cpp = tmp_path / "hdr.cpp"
+    cpp.write_text(src)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(cpp)])
