@@ -215,3 +215,28 @@ def test_golden_path_loop(oracle, golden):
         assert sha(frame) == g["sha_frames"][k]
         assert sha(oracle.accumulate(acc, k + 1, frame)) == g["sha_shown"][k]
     assert sha(acc) == g["sha_accum"]
+
+
+@pytest.mark.parametrize("seed,n", [(1, 2), (2, 17), (3, 64), (4, 300), (5, 1500), (6, 5000), (8, 40), (21, 700)])
+def test_oracle_equals_reference_on_odd_scenes(oracle, reflib, seed, n):
+    """The fuzzer's scenes (tests/test_fuzz.py: zero / tiny / huge radii, lattices of coincident centres, flat slabs,
+    axis-parallel and unnormalised rays) through the COMPILED REFERENCE: the oracle the product is fuzzed against must
+    itself be the reference on them.  Negative radii are added here: the product refuses them (flatten.c), the
+    oracle still has to reproduce what the reference does with them."""
+    from test_fuzz import odd_rays, odd_scene
+    rng = np.random.default_rng(seed)
+    s = odd_scene(rng, n)
+    if seed % 2 == 0:
+        s["r"][rng.integers(0, n, max(1, n // 20))] *= -1.0
+    depth0 = int(rng.choice([0, 0, 20, 36]))
+    sr, so = s.copy(), s.copy()
+    root, _ = reflib.build(sr, 0, n, depth0)
+    nodes = oracle.build(so, 0, n, depth0)
+    st = reflib.tree_stats(root, depth0)
+    assert st == oracle.tree_stats(nodes, depth0)
+    assert same(reflib.export_tree(root, sr, st["nodes"]), nodes) and same(sr, so)
+    rays = odd_rays(rng, so, n, 4000)
+    hr, _ = reflib.trace_bvh(root, sr, rays)
+    ho, _ = oracle.trace_bvh(nodes, so, n, rays)
+    assert_hits_equal(ho, hr, f"odd scene seed {seed} n {n} depth0 {depth0}")
+    reflib.free(root)
