@@ -365,3 +365,22 @@ def test_public_headers_are_strict_c99_and_cxx17(tmp_path):
     cpp = tmp_path / "hdr.cpp"
     cpp.write_text(src)
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(cpp)])
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the reference's own CPU path through oracle/_ref, or the oracle port) prints the
+    contract's JSON line without touching CUDA; a small scene keeps it to a few seconds here."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--spheres", "20000",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "closest_hit_grays_per_s" and d["unit"] == "Grays/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": "Grays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "rays per step" in cb["sample"]
+    assert "workload" in d["config"] and "20000" in d["config"]["workload"]
