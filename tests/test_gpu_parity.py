@@ -817,3 +817,29 @@ def test_c_example_reproduces_benchmark_counts(gpu, oracle, tmp_path):
     assert found == want, (found, want)
     rows = open(str(tmp_path / "benchmark_data.txt")).read().split()
     assert rows[0] == "5000" and rows[3] == "10000" and len(rows) == 6
+
+
+def test_bench_line_contract_small_scene(gpu):
+    """bench.py's own arm on a small scene: the driver contract's keys are present and consistent (the headline
+    numbers come from the default 1 M-sphere run, not from here)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from common import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"),
+                          "--spheres", "20000", "--steps", "3", "--warmup", "3", "--no-sweep", "--no-cpu"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["metric"] == "closest_hit_grays_per_s" and d["unit"] == "Grays/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] >= 3 and d["vs_baseline"] is None
+    assert abs(d["value"] - d["config"]["rays_per_step"] / d["ms_per_step"] / 1e6) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == "Grays/s" and e["d2h_bytes_per_step"] == 32 * d["config"]["rays_per_step"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert "20000" in d["config"]["workload"] and "l2" in d["config"]
+
