@@ -100,6 +100,23 @@ class HostEmul:
         stats = dict(zip(("rays", "inner_visits", "sphere_tests", "exact_box_tests", "hits", "max_stack", "max_visits"), map(int, st)))
         return hits, stats
 
+    def check_culling(self, h, rays, node_step=1, threads=8):
+        """(ray, box) pairs the reference's slab test accepts but an interior test rejects -- must be zero."""
+        rays = np.ascontiguousarray(rays)
+        out = (C.c_uint64 * 4)()
+        rc = self.lib.emul_check_culling(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), C.c_int(node_step), C.c_int(threads), out)
+        assert rc == 0
+        return dict(zip(("pairs", "accepted", "bad_binary", "bad_wide"), map(int, out)))
+
+    def check_frustum(self, h, cam, w, hgt, tile_w=16, tile_h=8, tile_step=1, node_step=1):
+        """(tile, box) pairs where the reference accepts the box for some ray of the tile but the tile's frustum
+        test rejects it -- must be zero."""
+        out = (C.c_uint64 * 4)()
+        rc = self.lib.emul_check_frustum(C.c_void_p(h), _ptr(cam), C.c_int(w), C.c_int(hgt), C.c_int(tile_w), C.c_int(tile_h),
+                                         C.c_int(tile_step), C.c_int(node_step), out)
+        assert rc == 0
+        return dict(zip(("pairs", "accepted", "bad", "bad_simple"), map(int, out)))
+
     def primary_rays(self, cam, w, h, y0=0, y1=None):
         y1 = h if y1 is None else y1
         out = np.zeros((y1 - y0) * w, RAY_DT)

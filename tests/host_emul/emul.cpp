@@ -340,3 +340,148 @@ extern "C" int emul_wide_trace(emul_bvh *e, const Ray *rays, int64_t n, gpu_hit 
     }
     return SAHBVH_OK;
 }
+
+/* ---- soundness of the interior (culling) tests, checked directly --------------------------------------------
+ * The design rests on one implication: whenever the REFERENCE's slab test (sah_box_exact, hit.c:49-82) accepts a
+ * box for a ray, every interior test the kernels use for that box accepts it too (with no best-t bound).  The
+ * parity tests only see a violation when the wrongly culled box held the winning hit; these checkers test the
+ * implication itself for every (ray, box) pair.  Rays with a zero / tiny direction component are skipped: there the
+ * reference accepts every slab and the kernels use the geometric rule whose (different) guarantee is argued in
+ * DESIGN.md section 2 and covered by the result-level tests. */
+static bool ray_is_regular(const Ray &q)
+{
+    return fabsf(q.direction.x) >= SAH_TINY_DIR && fabsf(q.direction.y) >= SAH_TINY_DIR && fabsf(q.direction.z) >= SAH_TINY_DIR;
+}
+
+struct cull_counts { unsigned long long pairs, accepted, bad_binary, bad_wide; };
+
+static void cull_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t hi, int node_step, cull_counts *out)
+{
+    const SahScene sc = scene_of(e);
+    int32_t fast[SAH_WIDE_STACK_MAX], slow[SAH_WIDE_STACK_MAX];
+    const SahStack stk = {fast, 1, SAH_WIDE_STACK_MAX, slow};
+    cull_counts c = {0, 0, 0, 0};
+    for (int64_t i = lo; i < hi; i++) {
+        if (!ray_is_regular(rays[i])) continue;
+        SahRay r;
+        sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
+                      rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, sc);
+        SahRay rw = r;
+        sah_ray_to_wide(rw);
+        /* binary flattened tree: both child records of every node_step-th node */
+        for (int64_t nd = i % node_step; nd < e->f.info.n_inner; nd += node_step)
+            for (int ch = 0; ch < 2; ch++) {
+                const float *q = e->f.nodes + (size_t)nd * 16 + ch * 8;
+                if (sah_f2i(q[6]) == SAHBVH_REF_NONE) continue;
+                c.pairs++;
+                if (!sah_box_exact(r, q[0], q[1], q[2], q[3], q[4], q[5])) continue;
+                c.accepted++;
+                float tn;
+                if (!sah_box_conservative(r, q[0], q[1], q[2], q[3], q[4], q[5], INFINITY, tn)) c.bad_binary++;
+            }
+        /* 4-wide quantised nodes: a child whose full-precision box the reference accepts must come out of
+         * sah_wide_visit (as the next node, on the stack, or parked as a pending leaf) */
+        for (int64_t nd = i % node_step; nd < e->w.n_wide; nd += node_step) {
+            uint32_t w[16];
+            memcpy(w, e->w.nodes + (size_t)nd * 16, 64);
+            bool want[4];
+            int n_want = 0;
+            for (int ch = 0; ch < 4; ch++) {
+                const float *q = e->w.full + (size_t)nd * 32 + ch * 8;
+                want[ch] = (int32_t)w[10 + ch] != SAHBVH_REF_NONE && sah_box_exact(r, q[0], q[1], q[2], q[3], q[4], q[5]);
+                n_want += want[ch];
+            }
+            if (!n_want) continue;
+            bool got[4] = {false, false, false, false};
+            int stall_at = -1;
+            for (int round = 0; round < 4; round++) {
+                int sp = 0;
+                int32_t pend0 = SAH_REF_NONE, pend1 = SAH_REF_NONE;
+                const int32_t next = sah_wide_visit<false>(rw, w, (int32_t)nd, stk, sp, INFINITY, pend0, pend1, stall_at, nullptr);
+                for (int ch = 0; ch < 4; ch++) {
+                    const int32_t ref = (int32_t)w[10 + ch];
+                    if (ref == SAHBVH_REF_NONE) continue;
+                    bool seen = ref == pend0 || ref == pend1 || (stall_at < 0 && ref >= 0 && ref == next);
+                    for (int k = 0; k < sp; k++) seen = seen || fast[k] == ref;
+                    got[ch] = got[ch] || seen;
+                }
+                if (stall_at < 0) break; /* a stalled visit parks the remaining leaves when it is repeated */
+            }
+            for (int ch = 0; ch < 4; ch++)
+                if (want[ch] && !got[ch]) c.bad_wide++;
+        }
+    }
+    *out = c;
+}
+
+extern "C" int emul_check_culling(emul_bvh *e, const Ray *rays, int64_t n, int node_step, int threads, unsigned long long *out4)
+{
+    int rc = ensure_wide(e);
+    if (rc != SAHBVH_OK) return rc;
+    if (threads < 1) threads = 1;
+    if (node_step < 1) node_step = 1;
+    std::vector<cull_counts> cnt((size_t)threads);
+    std::vector<std::thread> pool;
+    for (int k = 0; k < threads; k++)
+        pool.emplace_back(cull_range, e, rays, n * k / threads, n * (k + 1) / threads, node_step, &cnt[(size_t)k]);
+    for (auto &t : pool) t.join();
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    for (auto &c : cnt) { out4[0] += c.pairs; out4[1] += c.accepted; out4[2] += c.bad_binary; out4[3] += c.bad_wide; }
+    return SAHBVH_OK;
+}
+
+/* packet kernel: if the reference accepts a box for ANY regular ray of a pixel tile, the tile's frustum test
+ * (sah_frustum_box, and sah_frustum_box_simple where it applies) must accept the box */
+extern "C" int emul_check_frustum(emul_bvh *e, const Camera *cam, int width, int height, int tile_w, int tile_h, int tile_step,
+                                  int node_step, unsigned long long *out4)
+{
+    int rc = ensure_wide(e);
+    if (rc != SAHBVH_OK) return rc;
+    SahCamera c;
+    fill_camera(cam, width, height, &c);
+    const SahScene sc = scene_of(e);
+    unsigned long long pairs = 0, accepted = 0, bad = 0, bad_simple = 0;
+    int tile_no = 0;
+    for (int ty = 0; ty < height; ty += tile_h)
+        for (int tx = 0; tx < width; tx += tile_w, tile_no++) {
+            if (tile_no % tile_step) continue;
+            const int nx = std::min(tile_w, width - tx), ny = std::min(tile_h, height - ty), nr = nx * ny;
+            std::vector<SahRay> rr((size_t)nr);
+            std::vector<char> regular((size_t)nr);
+            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int i = 0; i < nr; i++) {
+                float dx, dy, dz;
+                sah_primary_dir(c, tx + i % nx, ty + i / nx, dx, dy, dz);
+                sah_ray_setup(rr[(size_t)i], c.px, c.py, c.pz, dx, dy, dz, sc);
+                regular[(size_t)i] = fabsf(dx) >= SAH_TINY_DIR && fabsf(dy) >= SAH_TINY_DIR && fabsf(dz) >= SAH_TINY_DIR;
+                mn[0] = fminf(mn[0], dx); mx[0] = fmaxf(mx[0], dx);
+                mn[1] = fminf(mn[1], dy); mx[1] = fmaxf(mx[1], dy);
+                mn[2] = fminf(mn[2], dz); mx[2] = fmaxf(mx[2], dz);
+            }
+            float ex = fmaxf(fabsf(c.px - sc.lo[0]), fabsf(c.px - sc.hi[0]));
+            float ey = fmaxf(fabsf(c.py - sc.lo[1]), fabsf(c.py - sc.hi[1]));
+            float ez = fmaxf(fabsf(c.pz - sc.lo[2]), fabsf(c.pz - sc.hi[2]));
+            float pad = sqrtf(ex * ex + ey * ey + ez * ez) * 0.001953125f + sc.r_max * 0.001953125f;
+            SahFrustumAxis FX, FY, FZ;
+            sah_frustum_axis_setup(FX, c.px, mn[0], mx[0], pad, sc.geometric_zero_axes != 0);
+            sah_frustum_axis_setup(FY, c.py, mn[1], mx[1], pad, sc.geometric_zero_axes != 0);
+            sah_frustum_axis_setup(FZ, c.pz, mn[2], mx[2], pad, sc.geometric_zero_axes != 0);
+            const bool simple = sah_frustum_simple(FX, FY, FZ);
+            for (int64_t nd = tile_no % node_step; nd < e->w.n_wide; nd += node_step)
+                for (int ch = 0; ch < 4; ch++) {
+                    const float *q = e->w.full + (size_t)nd * 32 + ch * 8;
+                    if (sah_f2i(q[6]) == SAHBVH_REF_NONE) continue;
+                    pairs++;
+                    bool any = false;
+                    for (int i = 0; i < nr && !any; i++)
+                        any = regular[(size_t)i] && sah_box_exact(rr[(size_t)i], q[0], q[1], q[2], q[3], q[4], q[5]);
+                    if (!any) continue;
+                    accepted++;
+                    float tn;
+                    if (!sah_frustum_box(FX, FY, FZ, q[0], q[1], q[2], q[3], q[4], q[5], INFINITY, tn)) bad++;
+                    if (simple && !sah_frustum_box_simple(FX, FY, FZ, q[0], q[1], q[2], q[3], q[4], q[5], INFINITY, tn)) bad_simple++;
+                }
+        }
+    out4[0] = pairs; out4[1] = accepted; out4[2] = bad; out4[3] = bad_simple;
+    return SAHBVH_OK;
+}
