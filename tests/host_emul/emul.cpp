@@ -345,15 +345,34 @@ extern "C" int emul_wide_trace(emul_bvh *e, const Ray *rays, int64_t n, gpu_hit 
  * The design rests on one implication: whenever the REFERENCE's slab test (sah_box_exact, hit.c:49-82) accepts a
  * box for a ray, every interior test the kernels use for that box accepts it too (with no best-t bound).  The
  * parity tests only see a violation when the wrongly culled box held the winning hit; these checkers test the
- * implication itself for every (ray, box) pair.  Rays with a zero / tiny direction component are skipped: there the
- * reference accepts every slab and the kernels use the geometric rule whose (different) guarantee is argued in
- * DESIGN.md section 2 and covered by the result-level tests. */
+ * implication itself for every (ray, box) pair.  For a ray with a zero / tiny direction component the reference
+ * accepts every slab on that axis while the kernels use the geometric rule, whose guarantee is
+ * narrower: no LEAF the reference could report -- own box accepted AND sphere test passed -- is rejected (the rule is
+ * monotone in the box, so the leaf's ancestors follow).  Such rays are checked against the leaves only. */
 static bool ray_is_regular(const Ray &q)
 {
     return fabsf(q.direction.x) >= SAH_TINY_DIR && fabsf(q.direction.y) >= SAH_TINY_DIR && fabsf(q.direction.z) >= SAH_TINY_DIR;
 }
 
 struct cull_counts { unsigned long long pairs, accepted, bad_binary, bad_wide; };
+
+/* for rays with a zero / tiny axis: does leaf `sidx` pass the reference's sphere test (hit.c:19-39)? */
+static bool leaf_reportable(const emul_bvh *e, const SahRay &r, int32_t sidx)
+{
+    if ((uint32_t)sidx >= (uint32_t)e->f.info.n_spheres) return false;
+    const float *s = e->f.spheres4 + (size_t)sidx * 4;
+    float t;
+    return sah_sphere_t(r, s[0], s[1], s[2], s[3], t);
+}
+
+static int32_t wide_leaf_sphere(const emul_bvh *e, int32_t ref)
+{
+    const uint32_t code = (uint32_t)~ref;
+    if (!(code & SAH_WIDE_SPECIAL)) return (int32_t)code;
+    const uint32_t k = code & ~SAH_WIDE_SPECIAL;
+    if (k >= (uint32_t)e->w.n_special) return -1;
+    return sah_f2i(e->w.special[(size_t)k * 8 + 6]);
+}
 
 static void cull_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t hi, int node_step, cull_counts *out)
 {
@@ -362,7 +381,7 @@ static void cull_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t h
     const SahStack stk = {fast, 1, SAH_WIDE_STACK_MAX, slow};
     cull_counts c = {0, 0, 0, 0};
     for (int64_t i = lo; i < hi; i++) {
-        if (!ray_is_regular(rays[i])) continue;
+        const bool regular = ray_is_regular(rays[i]);
         SahRay r;
         sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
                       rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, sc);
@@ -372,9 +391,11 @@ static void cull_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t h
         for (int64_t nd = i % node_step; nd < e->f.info.n_inner; nd += node_step)
             for (int ch = 0; ch < 2; ch++) {
                 const float *q = e->f.nodes + (size_t)nd * 16 + ch * 8;
-                if (sah_f2i(q[6]) == SAHBVH_REF_NONE) continue;
+                const int32_t ref = sah_f2i(q[6]);
+                if (ref == SAHBVH_REF_NONE || (!regular && ref >= 0)) continue;
                 c.pairs++;
                 if (!sah_box_exact(r, q[0], q[1], q[2], q[3], q[4], q[5])) continue;
+                if (!regular && !leaf_reportable(e, r, ~ref)) continue;
                 c.accepted++;
                 float tn;
                 if (!sah_box_conservative(r, q[0], q[1], q[2], q[3], q[4], q[5], INFINITY, tn)) c.bad_binary++;
@@ -388,7 +409,9 @@ static void cull_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t h
             int n_want = 0;
             for (int ch = 0; ch < 4; ch++) {
                 const float *q = e->w.full + (size_t)nd * 32 + ch * 8;
-                want[ch] = (int32_t)w[10 + ch] != SAHBVH_REF_NONE && sah_box_exact(r, q[0], q[1], q[2], q[3], q[4], q[5]);
+                const int32_t ref = (int32_t)w[10 + ch];
+                want[ch] = ref != SAHBVH_REF_NONE && (regular || ref < 0) && sah_box_exact(r, q[0], q[1], q[2], q[3], q[4], q[5]) &&
+                           (regular || leaf_reportable(e, r, wide_leaf_sphere(e, ref)));
                 n_want += want[ch];
             }
             if (!n_want) continue;

@@ -6,8 +6,9 @@
 
 Interior tests only cull, so this is exactly what makes "best over the leaves whose own exact tests pass" equal to
 the reference's recursion.  The parity tests notice a violation only if the culled box held the winning
-hit; here every (ray, box) pair is checked.  Rays with a zero / tiny direction component are excluded (geometric
-rule, argued in DESIGN.md section 2 and covered by result-level tests)."""
+hit; here every (ray, box) pair is checked.  For rays with a zero / tiny direction component the kernels use the
+geometric rule of DESIGN.md section 2; its guarantee -- no leaf the reference could report is rejected -- is checked
+on the leaves (axis_rays)."""
 import numpy as np
 import pytest
 
@@ -44,6 +45,26 @@ def grazing_rays(rng, nodes, m):
     return rays
 
 
+def axis_rays(rng, s, n, m):
+    """rays with one or two zero / tiny direction components that pass through (or just beside) spheres: the
+    geometric rule for such axes must keep every leaf the reference could report"""
+    from common import RAY_DT
+    pick = rng.integers(0, n, m)
+    c = s["c"][pick].astype(np.float64)
+    rad = np.abs(s["r"][pick].astype(np.float64))[:, None]
+    zero = rng.random((m, 3)) < 0.45
+    zero[zero.all(axis=1), 0] = False                                     # keep one free axis
+    zero[~zero.any(axis=1), 2] = True                                     # and at least one zero axis
+    off_zero = rng.uniform(-1.2, 1.2, size=(m, 3)) * rad                  # inside, grazing or just outside the slab
+    off_free = rng.normal(size=(m, 3)) * rng.choice([2.0, 30.0, 2000.0], size=(m, 1))
+    o = c + np.where(zero, off_zero, off_free)
+    d = np.where(zero, rng.choice([0.0, -0.0, 1e-35, -1e-41], size=(m, 3)), -off_free * rng.choice([1.0, 0.01], size=(m, 1)))
+    rays = np.zeros(m, RAY_DT)
+    rays["o"] = o.astype(np.float32)
+    rays["d"] = d.astype(np.float32)
+    return rays
+
+
 def _rays_for(oracle, em, h, n_bench=1500):
     cam = oracle.default_camera()
     prim = oracle.primary_rays(cam, 160, 90)
@@ -67,6 +88,8 @@ def test_interior_tests_never_reject_what_the_reference_accepts(oracle, em, kind
     assert r["accepted"] > 100 and r["bad_binary"] == 0 and r["bad_wide"] == 0, r
     r = em.check_culling(h, grazing_rays(np.random.default_rng(n), nodes, 3000))
     assert r["accepted"] > 100 and r["bad_binary"] == 0 and r["bad_wide"] == 0, r
+    r = em.check_culling(h, axis_rays(np.random.default_rng(n + 1), s, n, 4000))
+    assert r["accepted"] > 100 and r["bad_binary"] == 0 and r["bad_wide"] == 0, r
     f = em.check_frustum(h, cam, 320, 180, tile_step=1 if n <= 3000 else 5, node_step=1 if n <= 3000 else 3)
     assert f["accepted"] > 100 and f["bad"] == 0 and f["bad_simple"] == 0, f
     em.free(h)
@@ -79,7 +102,8 @@ def test_interior_tests_on_odd_scenes(oracle, em, seed, n):
     s = odd_scene(rng, n)
     depth0 = int(rng.choice([0, 0, 20, 36]))
     h = em.build(s, n, 0, n, depth0)
-    rays = np.concatenate([odd_rays(rng, s, n, 6000), grazing_rays(rng, em.build_tree(s.copy(), 0, n, depth0), 3000)])
+    rays = np.concatenate([odd_rays(rng, s, n, 6000), grazing_rays(rng, em.build_tree(s.copy(), 0, n, depth0), 3000),
+                           axis_rays(rng, s, n, 3000)])
     r = em.check_culling(h, rays)
     assert r["accepted"] > 100 and r["bad_binary"] == 0 and r["bad_wide"] == 0, r
     cam = oracle.default_camera()
