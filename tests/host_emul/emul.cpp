@@ -453,7 +453,7 @@ extern "C" int emul_check_culling(emul_bvh *e, const Ray *rays, int64_t n, int n
     return SAHBVH_OK;
 }
 
-/* packet kernel: if the reference accepts a box for ANY regular ray of a pixel tile, the tile's frustum test
+/* packet kernel: if the reference accepts a box for ANY ray of a pixel tile, the tile's frustum test
  * (sah_frustum_box, and sah_frustum_box_simple where it applies) must accept the box */
 extern "C" int emul_check_frustum(emul_bvh *e, const Camera *cam, int width, int height, int tile_w, int tile_h, int tile_step,
                                   int node_step, unsigned long long *out4)
@@ -495,9 +495,12 @@ extern "C" int emul_check_frustum(emul_bvh *e, const Camera *cam, int width, int
                     const float *q = e->w.full + (size_t)nd * 32 + ch * 8;
                     if (sah_f2i(q[6]) == SAHBVH_REF_NONE) continue;
                     pairs++;
+                    /* a ray with a zero / tiny axis counts only for a leaf it could report (see above) */
+                    const int32_t ref = sah_f2i(q[6]);
                     bool any = false;
                     for (int i = 0; i < nr && !any; i++)
-                        any = regular[(size_t)i] && sah_box_exact(rr[(size_t)i], q[0], q[1], q[2], q[3], q[4], q[5]);
+                        any = sah_box_exact(rr[(size_t)i], q[0], q[1], q[2], q[3], q[4], q[5]) &&
+                              (regular[(size_t)i] || (ref < 0 && leaf_reportable(e, rr[(size_t)i], ~ref)));
                     if (!any) continue;
                     accepted++;
                     float tn;
