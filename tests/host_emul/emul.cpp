@@ -511,3 +511,133 @@ extern "C" int emul_check_frustum(emul_bvh *e, const Camera *cam, int width, int
     out4[0] = pairs; out4[1] = accepted; out4[2] = bad; out4[3] = bad_simple;
     return SAHBVH_OK;
 }
+
+/* ---- best-t culling never loses the winner -------------------------------------------------------------------
+ * best_s = best_t (1 + 2^-9) + 2 r_max / |d| must leave every box on the root-to-leaf path of the reference's
+ * winner W acceptable, whatever was found before W.  Any earlier hit has t >= t_W, so the tightest bound a
+ * schedule can hold when it reaches W's path is best_s(t_W): the path is checked against exactly that bound
+ * (binary FMA test and 4-wide visit).  The winner is found the reference's way: exhaustive descent through the
+ * boxes its own slab test accepts (hit.c:91-109). */
+struct path_step { int32_t node; int child; };
+
+struct winner_search {
+    const emul_bvh *e;
+    const SahRay *r;
+    bool wide;
+    float best_t;
+    int32_t best_prim;
+    std::vector<path_step> cur;
+    std::vector<std::vector<path_step>> best_paths;   /* every leaf that yields the winning record: an empty leaf (Q3)
+                                                         aliases a sphere that also has a leaf of its own */
+};
+
+static void winner_descend(winner_search &ws, int32_t node)
+{
+    const int fan = ws.wide ? 4 : 2;
+    const float *rec = ws.wide ? ws.e->w.full + (size_t)node * 32 : ws.e->f.nodes + (size_t)node * 16;
+    for (int ch = 0; ch < fan; ch++) {
+        const float *q = rec + ch * 8;
+        const int32_t ref = sah_f2i(q[6]);
+        if (ref == SAHBVH_REF_NONE) continue;
+        if (!sah_box_exact(*ws.r, q[0], q[1], q[2], q[3], q[4], q[5])) continue;
+        ws.cur.push_back({node, ch});
+        if (ref >= 0) {
+            /* the twin keeps the BINARY tree's refs; the wide child index lives in the quantised node */
+            winner_descend(ws, ws.wide ? (int32_t)ws.e->w.nodes[(size_t)node * 16 + 10 + ch] : ref);
+        } else {
+            const int32_t idx = ~ref;
+            float t;
+            if ((uint32_t)idx < (uint32_t)ws.e->f.info.n_spheres) {
+                const float *s = ws.e->f.spheres4 + (size_t)idx * 4;
+                if (sah_sphere_t(*ws.r, s[0], s[1], s[2], s[3], t)) {
+                    if (ws.best_prim < 0 || t < ws.best_t || (t == ws.best_t && idx > ws.best_prim)) {
+                        ws.best_t = t;
+                        ws.best_prim = idx;
+                        ws.best_paths.clear();
+                        ws.best_paths.push_back(ws.cur);
+                    } else if (t == ws.best_t && idx == ws.best_prim) {
+                        ws.best_paths.push_back(ws.cur);
+                    }
+                }
+            }
+        }
+        ws.cur.pop_back();
+    }
+}
+
+struct bestt_counts { unsigned long long winners, steps, bad_binary, bad_wide, disagree; };
+
+static void bestt_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t hi, bestt_counts *out)
+{
+    const SahScene sc = scene_of(e);
+    int32_t fast[SAH_WIDE_STACK_MAX], slow[SAH_WIDE_STACK_MAX];
+    const SahStack stk = {fast, 1, SAH_WIDE_STACK_MAX, slow};
+    bestt_counts c = {0, 0, 0, 0, 0};
+    for (int64_t i = lo; i < hi; i++) {
+        SahRay r;
+        sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
+                      rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, sc);
+        SahRay rw = r;
+        sah_ray_to_wide(rw);
+        winner_search wb = {e, &r, false, 0.0f, -1, {}, {}};
+        winner_descend(wb, 0);
+        winner_search ww = {e, &r, true, 0.0f, -1, {}, {}};
+        winner_descend(ww, 0);
+        /* the record is safe if ONE of the leaves that produce it survives */
+        if (wb.best_prim != ww.best_prim || (wb.best_prim >= 0 && wb.best_t != ww.best_t)) c.disagree++;
+        if (wb.best_prim < 0) continue;
+        c.winners++;
+        const float best_s = F_FMA(wb.best_t, SAH_REL_CULL, r.cull_abs);
+        bool any_ok = false;
+        for (const auto &path : wb.best_paths) {
+            bool ok = true;
+            for (const path_step &p : path) {
+                const float *q = e->f.nodes + (size_t)p.node * 16 + p.child * 8;
+                float tn;
+                c.steps++;
+                ok = ok && sah_box_conservative(r, q[0], q[1], q[2], q[3], q[4], q[5], best_s, tn);
+            }
+            any_ok = any_ok || ok;
+        }
+        if (!any_ok) c.bad_binary++;
+        any_ok = false;
+        for (const auto &path : ww.best_paths) {
+            bool ok = true;
+            for (const path_step &p : path) {
+                uint32_t w[16];
+                memcpy(w, e->w.nodes + (size_t)p.node * 16, 64);
+                const int32_t want = (int32_t)w[10 + p.child];
+                bool got = false;
+                int stall_at = -1;
+                for (int round = 0; round < 4 && !got && want != SAHBVH_REF_NONE; round++) {   /* NONE: the leaf was dropped */
+                    int sp = 0;
+                    int32_t pend0 = SAH_REF_NONE, pend1 = SAH_REF_NONE;
+                    const int32_t next = sah_wide_visit<false>(rw, w, p.node, stk, sp, best_s, pend0, pend1, stall_at, nullptr);
+                    got = want == pend0 || want == pend1 || (stall_at < 0 && want >= 0 && want == next);
+                    for (int k = 0; k < sp; k++) got = got || fast[k] == want;
+                    if (stall_at < 0) break;
+                }
+                c.steps++;
+                ok = ok && got;
+            }
+            any_ok = any_ok || ok;
+        }
+        if (!any_ok) c.bad_wide++;
+    }
+    *out = c;
+}
+
+extern "C" int emul_check_best_t(emul_bvh *e, const Ray *rays, int64_t n, int threads, unsigned long long *out5)
+{
+    int rc = ensure_wide(e);
+    if (rc != SAHBVH_OK) return rc;
+    if (threads < 1) threads = 1;
+    std::vector<bestt_counts> cnt((size_t)threads);
+    std::vector<std::thread> pool;
+    for (int k = 0; k < threads; k++)
+        pool.emplace_back(bestt_range, e, rays, n * k / threads, n * (k + 1) / threads, &cnt[(size_t)k]);
+    for (auto &t : pool) t.join();
+    for (int k = 0; k < 5; k++) out5[k] = 0;
+    for (auto &c : cnt) { out5[0] += c.winners; out5[1] += c.steps; out5[2] += c.bad_binary; out5[3] += c.bad_wide; out5[4] += c.disagree; }
+    return SAHBVH_OK;
+}

@@ -12,7 +12,7 @@ on the leaves (axis_rays)."""
 import numpy as np
 import pytest
 
-from common import HostEmul
+from common import HostEmul, same
 from test_fuzz import odd_rays, odd_scene
 
 
@@ -111,3 +111,44 @@ def test_interior_tests_on_odd_scenes(oracle, em, seed, n):
     f = em.check_frustum(h, cam, 320, 200)
     assert f["bad"] == 0 and f["bad_simple"] == 0, f
     em.free(h)
+
+
+def limb_rays(rng, s, n, m):
+    """rays that graze spheres from near and far: at the limb the reference's FLOAT discriminant (hit.c:21-25) reports
+    hits whose t can precede the sphere's own box entry -- the case the 2 r_max / |d| term of the cull bound is for"""
+    from common import RAY_DT
+    pick = rng.integers(0, n, m)
+    c = s["c"][pick].astype(np.float64)
+    rad = np.abs(s["r"][pick].astype(np.float64))[:, None]
+    u = rng.normal(size=(m, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    w = np.cross(u, rng.normal(size=(m, 3)))
+    w /= np.linalg.norm(w, axis=1, keepdims=True)
+    dist = rng.choice([3.0, 100.0, 3000.0, 60000.0], size=(m, 1))
+    eps = rng.choice([0.0, 1e-6, -1e-6, 1e-4, -1e-4, 3e-3, -3e-3, -0.3], size=(m, 1))
+    o = c - u * dist + w * rad * (1.0 + eps)
+    rays = np.zeros(m, RAY_DT)
+    rays["o"] = o.astype(np.float32)
+    rays["d"] = (u * rng.choice([1.0, 1e-3, 25.0], size=(m, 1))).astype(np.float32)
+    return rays
+
+
+@pytest.mark.parametrize("kind,n,build", [("benchmark", 20000, (0, 20000, 0)), ("benchmark", 5000, (0, 4999, 20)),
+                                          ("random", 3000, (0, 3000, 0)), ("random", 200, (0, 200, 0)), ("odd", 1500, (0, 1500, 0))])
+def test_best_t_bound_never_culls_the_winners_path(oracle, em, kind, n, build):
+    """best_s = best_t (1 + 2^-9) + 2 r_max / |d|: every box on the path to the reference's winner passes the
+    interior tests under the bound of the winner's own t (the tightest bound any schedule can hold there)."""
+    rng = np.random.default_rng(n)
+    oracle.srand(5)
+    s = odd_scene(rng, n) if kind == "odd" else (oracle.scene_benchmark(n) if kind == "benchmark" else oracle.scene_random(n))
+    h = em.build(s, n, *build)
+    rays, _ = _rays_for(oracle, em, h, 3000)
+    rays = np.concatenate([rays, limb_rays(rng, s, n, 20000), axis_rays(rng, s, n, 3000), odd_rays(rng, s, n, 3000)])
+    r = em.check_best_t(h, rays)
+    assert r["winners"] > 1000 and r["bad_binary"] == 0 and r["bad_wide"] == 0 and r["disagree"] == 0, r
+    # and the winner found this way is the oracle's
+    want, _ = oracle.trace_bvh(oracle.build(s.copy(), *build), s, n, rays[:5000])
+    got, _ = em.trace(h, rays[:5000])
+    assert same(got, want)
+    em.free(h)
+
