@@ -111,10 +111,10 @@ class HostEmul:
     def check_best_t(self, h, rays, threads=8):
         """boxes on the path to the reference's winner that the best-t bound of the winner itself would cull -- must be zero"""
         rays = np.ascontiguousarray(rays)
-        out = (C.c_uint64 * 5)()
+        out = (C.c_uint64 * 6)()
         rc = self.lib.emul_check_best_t(C.c_void_p(h), _ptr(rays), C.c_int64(len(rays)), C.c_int(threads), out)
         assert rc == 0
-        return dict(zip(("winners", "steps", "bad_binary", "bad_wide", "disagree"), map(int, out)))
+        return dict(zip(("winners", "steps", "bad_binary", "bad_wide", "disagree", "bad_frustum"), map(int, out)))
 
     def check_frustum(self, h, cam, w, hgt, tile_w=16, tile_h=8, tile_step=1, node_step=1):
         """(tile, box) pairs where the reference accepts the box for some ray of the tile but the tile's frustum

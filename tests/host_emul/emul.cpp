@@ -565,20 +565,32 @@ static void winner_descend(winner_search &ws, int32_t node)
     }
 }
 
-struct bestt_counts { unsigned long long winners, steps, bad_binary, bad_wide, disagree; };
+struct bestt_counts { unsigned long long winners, steps, bad_binary, bad_wide, disagree, bad_frustum; };
 
 static void bestt_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t hi, bestt_counts *out)
 {
     const SahScene sc = scene_of(e);
     int32_t fast[SAH_WIDE_STACK_MAX], slow[SAH_WIDE_STACK_MAX];
     const SahStack stk = {fast, 1, SAH_WIDE_STACK_MAX, slow};
-    bestt_counts c = {0, 0, 0, 0, 0};
+    bestt_counts c = {0, 0, 0, 0, 0, 0};
     for (int64_t i = lo; i < hi; i++) {
         SahRay r;
         sah_ray_setup(r, rays[i].origin.x, rays[i].origin.y, rays[i].origin.z,
                       rays[i].direction.x, rays[i].direction.y, rays[i].direction.z, sc);
         SahRay rw = r;
         sah_ray_to_wide(rw);
+        /* the packet kernel's test for the one-ray tile {r}: a real tile's entry bound can only be smaller and its
+         * cull bound (max over the tile's rays) only larger, so passing here implies passing in any tile with r */
+        SahFrustumAxis FX, FY, FZ;
+        {
+            float ex = fmaxf(fabsf(r.ox - sc.lo[0]), fabsf(r.ox - sc.hi[0]));
+            float ey = fmaxf(fabsf(r.oy - sc.lo[1]), fabsf(r.oy - sc.hi[1]));
+            float ez = fmaxf(fabsf(r.oz - sc.lo[2]), fabsf(r.oz - sc.hi[2]));
+            float pad = sqrtf(ex * ex + ey * ey + ez * ez) * 0.001953125f + sc.r_max * 0.001953125f;
+            sah_frustum_axis_setup(FX, r.ox, r.dx, r.dx, pad, sc.geometric_zero_axes != 0);
+            sah_frustum_axis_setup(FY, r.oy, r.dy, r.dy, pad, sc.geometric_zero_axes != 0);
+            sah_frustum_axis_setup(FZ, r.oz, r.dz, r.dz, pad, sc.geometric_zero_axes != 0);
+        }
         winner_search wb = {e, &r, false, 0.0f, -1, {}, {}};
         winner_descend(wb, 0);
         winner_search ww = {e, &r, true, 0.0f, -1, {}, {}};
@@ -588,18 +600,23 @@ static void bestt_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t 
         if (wb.best_prim < 0) continue;
         c.winners++;
         const float best_s = F_FMA(wb.best_t, SAH_REL_CULL, r.cull_abs);
-        bool any_ok = false;
+        bool any_ok = false, any_ok_f = false;
         for (const auto &path : wb.best_paths) {
-            bool ok = true;
+            bool ok = true, ok_f = true;
             for (const path_step &p : path) {
                 const float *q = e->f.nodes + (size_t)p.node * 16 + p.child * 8;
                 float tn;
                 c.steps++;
                 ok = ok && sah_box_conservative(r, q[0], q[1], q[2], q[3], q[4], q[5], best_s, tn);
+                ok_f = ok_f && sah_frustum_box(FX, FY, FZ, q[0], q[1], q[2], q[3], q[4], q[5], best_s, tn);
+                if (sah_frustum_simple(FX, FY, FZ))
+                    ok_f = ok_f && sah_frustum_box_simple(FX, FY, FZ, q[0], q[1], q[2], q[3], q[4], q[5], best_s, tn);
             }
             any_ok = any_ok || ok;
+            any_ok_f = any_ok_f || ok_f;
         }
         if (!any_ok) c.bad_binary++;
+        if (!any_ok_f) c.bad_frustum++;
         any_ok = false;
         for (const auto &path : ww.best_paths) {
             bool ok = true;
@@ -627,7 +644,7 @@ static void bestt_range(const emul_bvh *e, const Ray *rays, int64_t lo, int64_t 
     *out = c;
 }
 
-extern "C" int emul_check_best_t(emul_bvh *e, const Ray *rays, int64_t n, int threads, unsigned long long *out5)
+extern "C" int emul_check_best_t(emul_bvh *e, const Ray *rays, int64_t n, int threads, unsigned long long *out6)
 {
     int rc = ensure_wide(e);
     if (rc != SAHBVH_OK) return rc;
@@ -637,7 +654,10 @@ extern "C" int emul_check_best_t(emul_bvh *e, const Ray *rays, int64_t n, int th
     for (int k = 0; k < threads; k++)
         pool.emplace_back(bestt_range, e, rays, n * k / threads, n * (k + 1) / threads, &cnt[(size_t)k]);
     for (auto &t : pool) t.join();
-    for (int k = 0; k < 5; k++) out5[k] = 0;
-    for (auto &c : cnt) { out5[0] += c.winners; out5[1] += c.steps; out5[2] += c.bad_binary; out5[3] += c.bad_wide; out5[4] += c.disagree; }
+    for (int k = 0; k < 6; k++) out6[k] = 0;
+    for (auto &c : cnt) {
+        out6[0] += c.winners; out6[1] += c.steps; out6[2] += c.bad_binary; out6[3] += c.bad_wide; out6[4] += c.disagree;
+        out6[5] += c.bad_frustum;
+    }
     return SAHBVH_OK;
 }

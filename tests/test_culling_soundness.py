@@ -145,7 +145,7 @@ def test_best_t_bound_never_culls_the_winners_path(oracle, em, kind, n, build):
     rays, _ = _rays_for(oracle, em, h, 3000)
     rays = np.concatenate([rays, limb_rays(rng, s, n, 20000), axis_rays(rng, s, n, 3000), odd_rays(rng, s, n, 3000)])
     r = em.check_best_t(h, rays)
-    assert r["winners"] > 1000 and r["bad_binary"] == 0 and r["bad_wide"] == 0 and r["disagree"] == 0, r
+    assert r["winners"] > 1000 and r["bad_binary"] == 0 and r["bad_wide"] == 0 and r["bad_frustum"] == 0 and r["disagree"] == 0, r
     # and the winner found this way is the oracle's
     want, _ = oracle.trace_bvh(oracle.build(s.copy(), *build), s, n, rays[:5000])
     got, _ = em.trace(h, rays[:5000])
