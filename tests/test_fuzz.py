@@ -56,6 +56,8 @@ def test_fuzz_host_core(oracle, emul, seed, n):
     so = s.copy()
     depth0 = int(rng.choice([0, 0, 20, 36]))
     nodes = oracle.build(so, 0, n, depth0)
+    st = s.copy()
+    assert same(emul.build_tree(st, 0, n, depth0), nodes) and same(st, so)   # binned host builder: same tree, same permutation
     h = emul.build(s, n, 0, n, depth0)
     assert same(s, so)
     rays = odd_rays(rng, so, n, 3000)
