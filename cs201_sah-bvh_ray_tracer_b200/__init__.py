@@ -36,11 +36,17 @@ EXPORTED_SYMBOLS = [
     "sahbvh_peer_alloc", "sahbvh_peer_open", "sahbvh_peer_close", "sahbvh_peer_free", "sahbvh_peer_signal", "sahbvh_peer_read_flags",
     "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     "sahbvh_host_alloc", "sahbvh_host_free", "sahbvh_host_pin", "sahbvh_host_unpin",
+    "gpu_trace_closest_hit_prims", "gpu_trace_closest_hit_dev_prims", "gpu_trace_primary_prims", "gpu_trace_primary_tprim",
+    "gpu_hits_from_prims", "sahbvh_set_keep_binary_tree", "sahbvh_peer_wait", "gpu_count_prims_dev",
+    "gpu_bvh_replicate", "gpu_bvh_build_replicated", "gpu_bvh_set_free", "gpu_bvh_set_size", "gpu_bvh_set_get",
+    "sahbvh_shard_range", "sahbvh_shard_rows", "gpu_trace_primary_multi", "gpu_trace_primary_prims_multi",
+    "gpu_trace_primary_prims_multi_dev", "gpu_trace_closest_hit_multi", "gpu_trace_closest_hit_prims_multi",
+    "gpu_benchmark_with_bvh_multi", "gpu_render_frame_multi",
     # include/sahbvh_ref_api.h
     "vec3_sub", "vec3_normalize", "vec3_dot", "vec3_add", "vec3_multiply", "vec3_cross", "vec3_random",
     "create_empty_aabb", "create_aabb_from_sphere", "combine_aabb", "get_aabb_surface_area", "evaluate_sah",
     "build_bvh_node", "free_bvh", "ray_sphere_intersect", "ray_aabb_intersect", "ray_bvh_intersect",
-    "get_camera_ray", "get_camera_ray_wh", "camera_update",
+    "get_camera_ray", "get_camera_ray_wh", "camera_update", "sahbvh_pixel_ray", "sahbvh_hit_from_prim", "sahbvh_scalar_forget",
     "random_float", "random_in_unit_sphere", "random_on_hemisphere",
     "create_benchmark_sphere", "create_sphere", "create_random_sphere",
     "sahbvh_fill_benchmark_scene", "sahbvh_fill_random_scene", "sahbvh_fill_benchmark_rays",
@@ -87,6 +93,10 @@ def _load():
     lib.build_bvh_node.restype = C.c_void_p
     lib.free_bvh.restype = None
     lib.gpu_bvh_free.restype = None
+    lib.gpu_bvh_set_free.restype = None
+    lib.gpu_bvh_set_get.restype = C.c_void_p
+    lib.sahbvh_shard_rows.restype = None
+    lib.sahbvh_shard_range.restype = None
     return lib
 
 
@@ -158,6 +168,14 @@ def build_tree(spheres: np.ndarray, start: int, end: int, depth: int = 0, mode: 
         cap = int(n)
         spheres[:] = backup                    # the build permuted the array; start again from the input order
     raise SahBvhError("sahbvh_build_tree: node count changed between two runs")
+
+
+def set_keep_binary_tree(keep: bool):
+    """Handles created afterwards keep (or drop) the 64-byte binary tree the PER_RAY / COOP / ONE_SHOT kernels read."""
+    _check(lib.sahbvh_set_keep_binary_tree(C.c_int(1 if keep else 0)), "sahbvh_set_keep_binary_tree")
+
+
+TPRIM_DT = np.dtype([("t", np.float32), ("prim", np.int32)])    # gpu_tprim
 
 
 def set_primary_mode(mode: int):
@@ -295,6 +313,71 @@ class GpuBvh:
         _check(lib.gpu_trace_primary(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
                                      C.c_void_p(out_ptr)), "gpu_trace_primary")
 
+    def trace_primary_prims(self, cam: np.ndarray, width: int, height: int, y0: int = 0, y1: int | None = None,
+                            out: np.ndarray | None = None) -> np.ndarray:
+        """gpu_trace_primary_prims: 4-byte primitive id per pixel into a host buffer (-1 = miss)."""
+        y1 = height if y1 is None else y1
+        if out is None:
+            out = np.empty((y1 - y0) * width, np.int32)
+        _check(lib.gpu_trace_primary_prims(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                           _ptr(out)), "gpu_trace_primary_prims")
+        return out
+
+    def trace_primary_prims_ptr(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, out_ptr: int):
+        _check(lib.gpu_trace_primary_prims(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                           C.c_void_p(out_ptr)), "gpu_trace_primary_prims")
+
+    def trace_primary_tprim(self, cam: np.ndarray, width: int, height: int, y0: int = 0, y1: int | None = None,
+                            out: np.ndarray | None = None) -> np.ndarray:
+        """gpu_trace_primary_tprim: {t, prim} per pixel (8 bytes) into a host buffer."""
+        y1 = height if y1 is None else y1
+        if out is None:
+            out = np.empty((y1 - y0) * width, TPRIM_DT)
+        _check(lib.gpu_trace_primary_tprim(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                           _ptr(out)), "gpu_trace_primary_tprim")
+        return out
+
+    def trace_primary_tprim_ptr(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, out_ptr: int):
+        _check(lib.gpu_trace_primary_tprim(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                           C.c_void_p(out_ptr)), "gpu_trace_primary_tprim")
+
+    def hits_from_prims(self, cam: np.ndarray, width: int, height: int, prims: np.ndarray, y0: int = 0,
+                        y1: int | None = None) -> np.ndarray:
+        """gpu_hits_from_prims: the full records of an id frame, rebuilt on demand (host buffers)."""
+        y1 = height if y1 is None else y1
+        prims = np.ascontiguousarray(prims, np.int32)
+        assert len(prims) == (y1 - y0) * width
+        out = np.empty(len(prims), HIT_DT)
+        _check(lib.gpu_hits_from_prims(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                       _ptr(prims), _ptr(out)), "gpu_hits_from_prims")
+        return out
+
+    def trace_closest_hit_prims(self, rays: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """gpu_trace_closest_hit_prims: 4-byte primitive id per ray (-1 = miss)."""
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == RAY_DT
+        if out is None:
+            out = np.empty(len(rays), np.int32)
+        _check(lib.gpu_trace_closest_hit_prims(self._h, _ptr(rays), C.c_int64(len(rays)), _ptr(out)), "gpu_trace_closest_hit_prims")
+        return out
+
+    def trace_closest_hit_prims_ptr(self, rays_ptr: int, n: int, out_ptr: int):
+        _check(lib.gpu_trace_closest_hit_prims(self._h, C.c_void_p(rays_ptr), C.c_int64(n), C.c_void_p(out_ptr)),
+               "gpu_trace_closest_hit_prims")
+
+    def trace_closest_hit_dev_prims(self, d_rays: int, n: int, d_prims: int, stream: int = 0):
+        _check(lib.gpu_trace_closest_hit_dev_prims(self._h, C.c_void_p(d_rays), C.c_int64(n), C.c_void_p(d_prims),
+                                                   C.c_void_p(stream)), "gpu_trace_closest_hit_dev_prims")
+
+    def benchmark_with_bvh_ptr(self, rays_ptr: int, n: int) -> int:
+        out = C.c_int64(0)
+        _check(lib.gpu_benchmark_with_bvh(self._h, C.c_void_p(rays_ptr), C.c_int64(n), C.byref(out)), "gpu_benchmark_with_bvh")
+        return int(out.value)
+
+    def render_frame_ptr(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, max_depth: int, seed: int, out_ptr: int):
+        _check(lib.gpu_render_frame(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
+                                    C.c_int(max_depth), C.c_uint64(seed), None, C.c_void_p(out_ptr)), "gpu_render_frame")
+
     def trace_brute_force(self, rays: np.ndarray) -> np.ndarray:
         rays = np.ascontiguousarray(rays)
         out = np.empty(len(rays), HIT_DT)
@@ -353,9 +436,9 @@ class GpuBvh:
 
     def trace_primary_dev_prims(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_out: int, d_prims: int,
                                 stream: int = 0):
-        """Full records to d_out and the 4-byte primitive-id buffer to d_prims (the all-gather slot)."""
+        """Full records to d_out (0 = none: ids only) and the 4-byte primitive-id buffer to d_prims."""
         _check(lib.gpu_trace_primary_dev_prims(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
-                                               C.c_void_p(d_out), C.c_void_p(d_prims), C.c_void_p(stream)),
+                                               C.c_void_p(d_out) if d_out else None, C.c_void_p(d_prims), C.c_void_p(stream)),
                "gpu_trace_primary_dev_prims")
 
     def hits_from_prims_dev(self, cam: np.ndarray, width: int, height: int, y0: int, y1: int, d_prims: int, d_out: int,
@@ -442,15 +525,149 @@ def generate_primary_rays(cam: np.ndarray, width: int, height: int, y0: int = 0,
     return out
 
 
-# ---- ray / row sharding across ranks: contiguous, no data-path collective ----
+# ---- ray / row sharding: contiguous, no data-path collective; the rule lives in the C library ----
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous ray range [lo, hi) of rank ``rank`` out of ``world`` (sizes differ by at most 1)."""
-    return n * rank // world, n * (rank + 1) // world
+    """Contiguous ray range [lo, hi) of part ``rank`` out of ``world`` (sizes differ by at most 1)."""
+    lo, hi = C.c_int64(), C.c_int64()
+    lib.sahbvh_shard_range(C.c_int64(n), C.c_int(rank), C.c_int(world), C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
 
 
-def shard_rows(height: int, rank: int, world: int, align: int = 8) -> tuple[int, int]:
-    """Row band [y0, y1) of a frame; bands are multiples of ``align`` rows (the kernel's CTA tile
-    height) except possibly the last, so no CTA straddles two ranks."""
-    blocks = (height + align - 1) // align
-    b0, b1 = blocks * rank // world, blocks * (rank + 1) // world
-    return min(b0 * align, height), min(b1 * align, height)
+def shard_rows(height: int, rank: int, world: int) -> tuple[int, int]:
+    """Row band [y0, y1) of a frame: whole 16-row blocks (the packet kernel's CTA group), so no block straddles two parts."""
+    y0, y1 = C.c_int(), C.c_int()
+    lib.sahbvh_shard_rows(C.c_int(height), C.c_int(rank), C.c_int(world), C.byref(y0), C.byref(y1))
+    return int(y0.value), int(y1.value)
+
+
+def peer_wait(flags_ptr: int, n: int, value: int, timeout_ms: int = 0, status_ptr: int = 0, stream: int = 0):
+    _check(lib.sahbvh_peer_wait(C.c_void_p(flags_ptr), C.c_int(n), C.c_uint64(value), C.c_uint32(timeout_ms),
+                                C.c_void_p(status_ptr) if status_ptr else None, C.c_void_p(stream)), "sahbvh_peer_wait")
+
+
+def count_prims_dev(d_prims: int, n: int, d_count: int, stream: int = 0):
+    _check(lib.gpu_count_prims_dev(C.c_void_p(d_prims), C.c_int64(n), C.c_void_p(d_count), C.c_void_p(stream)), "gpu_count_prims_dev")
+
+
+HITRECORD_DT = np.dtype([("t", np.float32), ("point", np.float32, 3), ("normal", np.float32, 3), ("hit_something", np.int32),
+                         ("object", np.uint64)])    # HitRecord, hit.h:8-14 (40 bytes)
+
+
+class _Vec3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class _Ray(C.Structure):
+    _fields_ = [("o", _Vec3), ("d", _Vec3)]
+
+
+class _HitRecord(C.Structure):
+    _fields_ = [("t", C.c_float), ("p", _Vec3), ("n", _Vec3), ("hit", C.c_int), ("obj", C.c_void_p)]
+
+
+def hit_from_prim(cam: np.ndarray, width: int, height: int, x: int, y: int, spheres: np.ndarray, prim: int):
+    """sahbvh_hit_from_prim(sahbvh_pixel_ray(cam, W, H, x, y), spheres, prim): the HitRecord of one pixel, derived on the host."""
+    lib.sahbvh_pixel_ray.restype = _Ray
+    lib.sahbvh_pixel_ray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.sahbvh_hit_from_prim.restype = _HitRecord
+    lib.sahbvh_hit_from_prim.argtypes = [_Ray, C.c_void_p, C.c_int32]
+    ray = lib.sahbvh_pixel_ray(cam.ctypes.data, width, height, x, y)
+    return lib.sahbvh_hit_from_prim(ray, spheres.ctypes.data, prim)
+
+
+class GpuBvhSet:
+    """Owner of one ``gpu_bvh_set*``: N replicas of a tree in ONE process (gpu_bvh_replicate)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def replicate(cls, bvh: GpuBvh, devices: list[int]) -> "GpuBvhSet":
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib.gpu_bvh_replicate(bvh._h, arr, C.c_int(len(devices)), C.byref(h)), "gpu_bvh_replicate")
+        return cls(h)
+
+    @classmethod
+    def build(cls, spheres: np.ndarray, n_total: int, start: int, end: int, depth: int, devices: list[int]) -> "GpuBvhSet":
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib.gpu_bvh_build_replicated(_ptr(spheres), C.c_int(n_total), C.c_int(start), C.c_int(end), C.c_int(depth),
+                                            arr, C.c_int(len(devices)), C.byref(h)), "gpu_bvh_build_replicated")
+        return cls(h)
+
+    def close(self):
+        if self._h:
+            lib.gpu_bvh_set_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self) -> int:
+        return int(lib.gpu_bvh_set_size(self._h))
+
+    def member_info(self, i: int) -> dict:
+        info = BvhInfo()
+        _check(lib.gpu_bvh_get_info(C.c_void_p(lib.gpu_bvh_set_get(self._h, C.c_int(i))), C.byref(info)), "gpu_bvh_get_info")
+        return info.as_dict()
+
+    def trace_primary(self, cam, width, height, out=None):
+        if out is None:
+            out = np.empty(width * height, HIT_DT)
+        _check(lib.gpu_trace_primary_multi(self._h, _ptr(cam), C.c_int(width), C.c_int(height), _ptr(out)), "gpu_trace_primary_multi")
+        return out
+
+    def trace_primary_prims(self, cam, width, height, out=None):
+        if out is None:
+            out = np.empty(width * height, np.int32)
+        _check(lib.gpu_trace_primary_prims_multi(self._h, _ptr(cam), C.c_int(width), C.c_int(height), _ptr(out)),
+               "gpu_trace_primary_prims_multi")
+        return out
+
+    def trace_primary_prims_ptr(self, cam, width, height, out_ptr: int):
+        _check(lib.gpu_trace_primary_prims_multi(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_void_p(out_ptr)),
+               "gpu_trace_primary_prims_multi")
+
+    def trace_primary_prims_dev(self, cam, width, height, d_prims: int, root_stream: int = 0):
+        _check(lib.gpu_trace_primary_prims_multi_dev(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_void_p(d_prims),
+                                                     C.c_void_p(root_stream)), "gpu_trace_primary_prims_multi_dev")
+
+    def trace_closest_hit(self, rays, out=None):
+        rays = np.ascontiguousarray(rays)
+        if out is None:
+            out = np.empty(len(rays), HIT_DT)
+        _check(lib.gpu_trace_closest_hit_multi(self._h, _ptr(rays), C.c_int64(len(rays)), _ptr(out)), "gpu_trace_closest_hit_multi")
+        return out
+
+    def trace_closest_hit_prims(self, rays, out=None):
+        rays = np.ascontiguousarray(rays)
+        if out is None:
+            out = np.empty(len(rays), np.int32)
+        _check(lib.gpu_trace_closest_hit_prims_multi(self._h, _ptr(rays), C.c_int64(len(rays)), _ptr(out)),
+               "gpu_trace_closest_hit_prims_multi")
+        return out
+
+    def benchmark_with_bvh(self, rays) -> int:
+        rays = np.ascontiguousarray(rays)
+        out = C.c_int64(0)
+        _check(lib.gpu_benchmark_with_bvh_multi(self._h, _ptr(rays), C.c_int64(len(rays)), C.byref(out)), "gpu_benchmark_with_bvh_multi")
+        return int(out.value)
+
+    def render_frame(self, cam, width, height, max_depth=5, seed=0, samples=None, out=None):
+        if out is None:
+            out = np.empty((width * height, 4), np.uint8)
+        sp = None
+        if samples is not None:
+            sp = np.ascontiguousarray(samples, np.float32)
+            assert sp.shape == (width * height, max_depth, 3)
+        _check(lib.gpu_render_frame_multi(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(max_depth), C.c_uint64(seed),
+                                          _ptr(sp) if sp is not None else None, _ptr(out)), "gpu_render_frame_multi")
+        return out
+
+    def render_frame_ptr(self, cam, width, height, max_depth, seed, out_ptr: int):
+        _check(lib.gpu_render_frame_multi(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(max_depth), C.c_uint64(seed),
+                                          None, C.c_void_p(out_ptr)), "gpu_render_frame_multi")

@@ -1067,19 +1067,30 @@ static int gb_build(sah_tree *t, Sphere *spheres, int n_total, int start, int en
     lap("preorder renumbering + sphere permutation");
     if (parts) {
         GB_TRY(cudaMemcpy(&h_ctr, d_ctr, sizeof h_ctr, cudaMemcpyDeviceToHost));
-        GB_TRY(cudaMemcpy(spheres + start, d_out_sph, (size_t)m * sizeof(Sphere), cudaMemcpyDeviceToHost));
-        lap("D2H permuted spheres");
         Sphere *d_all = d_out_sph;
         Sphere *d_all_owned = nullptr;
         if (start != 0 || end != n_total) { /* indices are global: the kernels need the whole array */
             GB_TRY(cudaMalloc((void **)&d_all_owned, (size_t)n_total * sizeof(Sphere)));
             cudaError_t e = cudaMemcpy(d_all_owned, spheres, (size_t)n_total * sizeof(Sphere), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(d_all_owned + start, d_out_sph, (size_t)m * sizeof(Sphere), cudaMemcpyDeviceToDevice);
             if (e != cudaSuccess) { cudaFree(d_all_owned); sahbvh_set_error("gpu builder: %s", cu_errstr(e)); rc = SAHBVH_E_CUDA; goto done; }
             d_all = d_all_owned;
         }
         rc = flatten_and_collapse(d_pre, h_ctr.nodes, h_ctr.max_depth, d_all, n_total, parts, timing);
         cudaFree(d_all_owned);
         lap("flatten + wide collapse (device)");
+        /* the caller's array is permuted only once nothing can fail any more: on an error, or when the host
+         * pipeline takes over (rc == 1), it still holds the input order the host builder expects */
+        if (rc == SAHBVH_OK) {
+            cudaError_t e = cudaMemcpy(spheres + start, d_out_sph, (size_t)m * sizeof(Sphere), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                sahbvh_set_error("gpu builder: %s", cu_errstr(e));
+                gpu_bvh_parts_release(parts);
+                rc = SAHBVH_E_CUDA;
+            }
+            lap("D2H permuted spheres");
+        }
         goto done;
     }
     if (t->cap < h_ctr.nodes) {

@@ -71,8 +71,23 @@ static inline const char *cu_errstr(cudaError_t e)
 
 SahScene sahbvh_make_scene(const gpu_bvh_info &info);
 void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c);
-int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count);
+/* d_out != NULL: 32-byte records; d_out == NULL: 4-byte primitive ids into d_prims (4-wide kernel only) */
+int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count, void *d_prims = nullptr);
 int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
-                          cudaStream_t st, bool count, void *d_ids, int ids_prim_only);
+                          cudaStream_t st, bool count, void *d_ids, int ids_mode);
+/* what the primary kernels write to d_ids */
+#define SAH_IDS_NONE 0
+#define SAH_IDS_PRIM 1   /* int32 primitive id per pixel (-1 = miss) */
+#define SAH_IDS_TPRIM 2  /* {float t, int32 prim} per pixel */
+/* host-buffer frames: what goes back over PCIe per pixel */
+#define HOSTFMT_RECORDS 0 /* gpu_hit, 32 B */
+#define HOSTFMT_PRIMS 1   /* int32 primitive id, 4 B */
+#define HOSTFMT_TPRIM 2   /* {float t, int32 prim}, 8 B */
+int sahbvh_primary_host_enqueue(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *out, int fmt);
+int sahbvh_primary_host_wait(gpu_bvh *b);
+extern "C" int sahbvh_set_packet_dfs_from(int v); /* diagnostic, see sahbvh_kernels.cu */
+/* the 64-byte binary tree is only read by the selectable binary-tree kernels: it is built from the 4-wide twin on
+ * first use instead of being kept in every handle */
+int sahbvh_need_binary_tree(gpu_bvh *b);
 
 #endif

@@ -306,6 +306,28 @@ HitRecord ray_bvh_intersect(Ray ray, BVHNode *node)
     return rec;
 }
 
+/* ------------------------------------------------------------------ lazily derived hit fields */
+/* main.c:362-365 for one pixel of a width x height frame */
+Ray sahbvh_pixel_ray(const Camera *cam, int width, int height, int x, int y)
+{
+    float aspect = (float)width / (float)height;
+    float u = ((float)x / (float)width - 0.5f) * aspect;
+    float v = (float)y / (float)height - 0.5f;
+    return get_camera_ray_wh(cam, u, -v, width, height);
+}
+
+/* The HitRecord (hit.h:8-14) ray_bvh_intersect returned for `ray`, given only the index of the sphere it hit:
+ * t, point and normal are pure functions of the ray and that sphere (hit.c:19-39 evaluated once more on the
+ * winner), so a caller that keeps the 4-byte id frame derives the other fields here, on demand, bit for bit.
+ * prim < 0 (miss) gives the all-zero record of hit.c:92. */
+HitRecord sahbvh_hit_from_prim(Ray ray, Sphere *spheres, int32_t prim)
+{
+    HitRecord rec;
+    memset(&rec, 0, sizeof rec);
+    if (prim < 0 || !spheres) return rec;
+    return ray_sphere_intersect(ray, &spheres[prim]);
+}
+
 /* ------------------------------------------------------------------ frame output (in place of SDL_RenderDrawPoint) */
 int sahbvh_write_ppm(const char *path, const uint8_t *rgba, int width, int height)
 {

@@ -117,7 +117,9 @@ k_shade(const gpu_hit *__restrict__ hits, long long n_rays, const int32_t *__res
                     const float *s = samples + (p * max_depth + k) * 3;
                     sx = s[0]; sy = s[1]; sz = s[2];
                 } else {
-                    random_in_unit_sphere_dev(seed, (uint64_t)p, (uint32_t)k, sx, sy, sz);
+                    /* keyed by the pixel's index in the WHOLE frame: a frame rendered in row bands (several devices) equals the
+                     * frame rendered in one call */
+                    random_in_unit_sphere_dev(seed, (uint64_t)p + (uint64_t)y0 * (uint64_t)width, (uint32_t)k, sx, sy, sz);
                 }
                 const float nx = h1.y, ny = h1.z, nz = h1.w;
                 const float dot = F_ADD(F_ADD(F_MUL(sx, nx), F_MUL(sy, ny)), F_MUL(sz, nz)); /* vec3.c:26-28 */
@@ -231,9 +233,11 @@ extern "C" int gpu_render_frame_dev(gpu_bvh *b, const Camera *cam, int width, in
     }
     const long long n_pixels = (long long)(y1 - y0) * width;
     if (n_pixels == 0) return SAHBVH_OK;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (prev != b->device) CU_TRY(cudaSetDevice(b->device));
+    DeviceGuard guard(b->device);
+    if (!guard.ok) {
+        sahbvh_set_error("gpu_render_frame: cudaSetDevice(%d) failed", b->device);
+        return SAHBVH_E_CUDA;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = SAHBVH_OK;
     do {
@@ -249,7 +253,7 @@ extern "C" int gpu_render_frame_dev(gpu_bvh *b, const Camera *cam, int width, in
         if (rc != SAHBVH_OK) break;
         SahCamera c;
         sahbvh_make_camera(cam, width, height, &c);
-        rc = sahbvh_launch_primary(b, cam, width, height, y0, y1, rb.hits, st, false, nullptr, 0);
+        rc = sahbvh_launch_primary(b, cam, width, height, y0, y1, rb.hits, st, false, nullptr, SAH_IDS_NONE);
         if (rc != SAHBVH_OK) break;
         long long n_rays = n_pixels;
         int cur = 0;
@@ -284,22 +288,24 @@ extern "C" int gpu_render_frame_dev(gpu_bvh *b, const Camera *cam, int width, in
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e)); rc = SAHBVH_E_CUDA; }
     } while (0);
-    if (prev >= 0 && prev != b->device) cudaSetDevice(prev);
     return rc;
 }
 
 extern "C" int gpu_render_frame(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, int max_depth,
                                 uint64_t seed, const Vec3 *samples, uint8_t *rgba_out)
 {
-    if (!b || !rgba_out || width <= 0 || y1 < y0) {
+    /* everything is validated before the first allocation (the _dev call repeats the same checks) */
+    if (!b || !cam || !rgba_out || width <= 0 || height <= 0 || y0 < 0 || y1 < y0 || y1 > height || max_depth < 0 || max_depth > 64) {
         sahbvh_set_error("gpu_render_frame: bad arguments");
         return SAHBVH_E_ARG;
     }
     const long long n_pixels = (long long)(y1 - y0) * width;
     if (n_pixels == 0) return SAHBVH_OK;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (prev != b->device) CU_TRY(cudaSetDevice(b->device));
+    DeviceGuard guard(b->device);
+    if (!guard.ok) {
+        sahbvh_set_error("gpu_render_frame: cudaSetDevice(%d) failed", b->device);
+        return SAHBVH_E_CUDA;
+    }
     void *d_samples = nullptr, *d_rgba = nullptr;
     int rc = SAHBVH_OK;
     cudaError_t e = cudaMalloc(&d_rgba, (size_t)n_pixels * 4);
@@ -323,7 +329,6 @@ extern "C" int gpu_render_frame(gpu_bvh *b, const Camera *cam, int width, int he
     }
     cudaFree(d_samples);
     cudaFree(d_rgba);
-    if (prev >= 0 && prev != b->device) cudaSetDevice(prev);
     return rc;
 }
 

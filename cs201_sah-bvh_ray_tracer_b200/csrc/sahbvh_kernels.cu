@@ -29,12 +29,30 @@ static_assert(sizeof(SahHit) == sizeof(gpu_hit), "hit record");
 static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 
 #define TRACE_THREADS 128
+#ifndef SAHBVH_HOST_DIRECT_DEFAULT
+#define SAHBVH_HOST_DIRECT_DEFAULT 0
+#endif
 #define PRIMARY_THREADS 256 /* 32 x 8 pixels per CTA, one 8x4 tile per warp */
 
 std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_PACKET};
 static std::atomic<int> g_ray_mode{SAHBVH_RAYS_WIDE};
 static std::atomic<int> g_build_mode{SAHBVH_BUILD_DEVICE};
+static std::atomic<int> g_keep_binary{0};
+
+extern "C" int sahbvh_set_keep_binary_tree(int keep)
+{
+    g_keep_binary.store(keep ? 1 : 0);
+    return SAHBVH_OK;
+}
+
+int sahbvh_need_binary_tree(gpu_bvh *b)
+{
+    if (b->d_nodes) return SAHBVH_OK;
+    sahbvh_set_error("this handle was created without the 64-byte binary tree (only SAHBVH_PRIMARY_PER_RAY, SAHBVH_RAYS_COOP and "
+                     "SAHBVH_RAYS_ONE_SHOT read it): call sahbvh_set_keep_binary_tree(1) before gpu_bvh_upload / gpu_bvh_build");
+    return SAHBVH_E_ARG;
+}
 
 extern "C" int sahbvh_set_build_mode(int mode)
 {
@@ -261,8 +279,10 @@ template <bool COUNT>
 __global__ void __launch_bounds__(WIDE_WARPS * 32, WIDE_MIN_BLOCKS)
 k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ spheres4, const float *__restrict__ special,
                   int n_special, SahScene sc, const float *__restrict__ rays, long long n, gpu_hit *__restrict__ out,
-                  unsigned long long *next_ray, unsigned long long *counters)
+                  int32_t *__restrict__ prims_out, unsigned long long *next_ray, unsigned long long *counters)
 {
+    /* out != NULL: 32-byte records; else prims_out receives the 4-byte primitive id per ray (point and normal are
+     * never computed: sahbvh_hit_from_prim / gpu_hits_from_prims derive them on demand) */
     __shared__ int32_t s_stack[WIDE_FAST_STACK][WIDE_WARPS * 32];
     int32_t slow[SAH_WIDE_STACK_MAX - WIDE_FAST_STACK];
     const SahStack stk = {&s_stack[0][threadIdx.x], WIDE_WARPS * 32, WIDE_FAST_STACK, slow};
@@ -297,15 +317,19 @@ k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ 
             if (node < SAH_NODE_DONE) node = -2 - node;
             /* 2. finished rays: store the record */
             if (node == SAH_NODE_DONE && ray_idx >= 0) {
-                SahHit h;
-                if (best_prim >= 0) {
-                    const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + best_prim);
-                    sah_finish_hit(r, best_t, best_prim, s.x, s.y, s.z, h);
-                    if (COUNT) hits++;
+                if (out) {
+                    SahHit h;
+                    if (best_prim >= 0) {
+                        const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + best_prim);
+                        sah_finish_hit(r, best_t, best_prim, s.x, s.y, s.z, h);
+                    } else {
+                        sah_miss(h);
+                    }
+                    store_hit(out + ray_idx, h);
                 } else {
-                    sah_miss(h);
+                    prims_out[ray_idx] = best_prim;
                 }
-                store_hit(out + ray_idx, h);
+                if (COUNT && best_prim >= 0) hits++;
                 ray_idx = -1;
                 if (COUNT) atomicMax(&counters[5], cnt.inner - visits0);
             }
@@ -360,7 +384,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(PRIMARY_THREADS)
 k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                 SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
-                int ids_prim_only, unsigned long long *counters)
+                int ids_mode, unsigned long long *counters)
 {
     int32_t stack[SAH_STACK_MAX];
     SahCounters cnt = {0, 0, 0, 0};
@@ -376,11 +400,9 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
         SahHit h;
         sah_trace_one<COUNT>(nodes, spheres4, sc.n_spheres, r, stack, 1, h, &cnt);
         const size_t pix = (size_t)(y - y0) * (size_t)width + (size_t)x;
-        store_hit(out + pix, h);
-        if (ids) {
-            if (ids_prim_only) reinterpret_cast<int32_t *>(ids)[pix] = h.prim;
-            else ids[pix] = make_float2(h.t, __int_as_float(h.prim));
-        }
+        if (out) store_hit(out + pix, h);
+        if (ids_mode == SAH_IDS_PRIM) reinterpret_cast<int32_t *>(ids)[pix] = h.prim;
+        else if (ids_mode == SAH_IDS_TPRIM) ids[pix] = make_float2(h.t, __int_as_float(h.prim));
         if (COUNT) hits += (h.prim >= 0);
     }
     if (COUNT) flush_counters(cnt, hits, counters);
@@ -401,15 +423,11 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
  * (and, for a would-be winner, the reference-exact leaf box test) on each candidate, so the
  * result is the same "best over leaves whose own tests pass" as the per-ray kernel.
  */
-#ifndef PKT_WARPS
-#define PKT_WARPS 4
-#endif
+#define PKT_WARPS 4        /* the block's 4 warps own a 2x2 group of tiles = 32 x 16 pixels (their frusta overlap more than a 4x1 strip's) */
 #ifndef PKT_STACK
 #define PKT_STACK 512
 #endif
-#ifndef PKT_K
-#define PKT_K 4 /* rays per lane: tile = 16 x (2*PKT_K) pixels */
-#endif
+#define PKT_K 4            /* rays per lane: tile = 16 x (2*PKT_K) pixels; 16x12 and 16x16 tiles measured slower */
 #define PKT_TILE_H (2 * PKT_K)
 #ifndef PKT_UNROLL
 #define PKT_UNROLL 4 /* per-ray loops: rolled (1) measures the same within 1%; the state is in shared memory either way */
@@ -418,9 +436,29 @@ static constexpr int kPktUnroll = PKT_UNROLL;
 #ifndef PKT_MIN_BLOCKS
 #define PKT_MIN_BLOCKS 8
 #endif
-#ifndef PKT_BLOCK_2X2
-#define PKT_BLOCK_2X2 (PKT_WARPS == 4)
-#endif
+/* Stack discipline (per-warp shared-memory stack of PKT_STACK refs, unchecked pushes): while top <= dfs_from a
+ * step pops up to 8 entries and pushes at most 32 (net +24); above dfs_from it pops ONE entry (plain DFS: net +3
+ * per wide level, and the tree has at most `depth` levels).  With dfs_from = PKT_STACK - 32 - 3*(depth + 2) the
+ * stack never holds more than dfs_from + 24 + 3*depth <= PKT_STACK - 14 entries, whatever the tree looks like
+ * (depth <= 62: flatten.c refuses deeper trees).  sahbvh_packet_dfs_from() computes it at launch. */
+static std::atomic<int> g_pkt_dfs_override{0};
+/* diagnostic: force the threshold (0 = derive it from the tree depth); tests use it to run whole frames in DFS mode
+ * and to check the stack bound dfs_from + 24 + 3*depth against gpu_trace_stats.max_stack */
+extern "C" int sahbvh_set_packet_dfs_from(int v)
+{
+    if (v < 0 || v > PKT_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2)) return SAHBVH_E_ARG;
+    g_pkt_dfs_override.store(v);
+    return SAHBVH_OK;
+}
+static int sahbvh_packet_dfs_from(int tree_depth)
+{
+    if (g_pkt_dfs_override.load() > 0) return g_pkt_dfs_override.load();
+    int d = tree_depth < 1 ? 1 : tree_depth;
+    if (d > SAHBVH_STACK_MAX) d = SAHBVH_STACK_MAX;
+    const int v = PKT_STACK - 32 - 3 * (d + 2);
+    return v < 8 ? 8 : v;
+}
+static_assert(PKT_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_STACK too small for the deepest admissible tree");
 
 __device__ __forceinline__ float warp_min(float v)
 {
@@ -433,11 +471,22 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
-template <bool COUNT>
+/* 32-byte record with ONE 256-bit store (sm_100 st.global.v8): a warp writing a 32-pixel row emits 1 KiB contiguous */
+__device__ __forceinline__ void store_hit256(gpu_hit *out, const SahHit &h)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out), "r"(__float_as_uint(h.t)), "r"((uint32_t)h.prim),
+                 "r"(__float_as_uint(h.px)), "r"(__float_as_uint(h.py)), "r"(__float_as_uint(h.pz)), "r"(__float_as_uint(h.nx)),
+                 "r"(__float_as_uint(h.ny)), "r"(__float_as_uint(h.nz))
+                 : "memory");
+}
+
+/* RECORDS: write the 32-byte hit records to `out` (else `out` is not touched and point/normal are never computed).
+ * ids_mode: SAH_IDS_NONE / SAH_IDS_PRIM (int32 per pixel) / SAH_IDS_TPRIM ({float t, int32 prim} per pixel) into `ids`. */
+template <bool COUNT, bool RECORDS>
 __global__ void __launch_bounds__(PKT_WARPS * 32, PKT_MIN_BLOCKS)
 k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                        SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
-                       int ids_prim_only, unsigned long long *counters)
+                       int ids_mode, int dfs_from, unsigned long long *counters)
 {
     /* The traversal loop is a chain of dependent node fetches, so it needs resident warps more than registers:
      * the per-ray state (direction, d.d, best t, best index of the lane's 4 rays) lives in shared memory -- it is
@@ -453,18 +502,11 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
     const int tiles_x = (width + 15) >> 4, tiles_y = (y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H;
     SahCounters cnt = {0, 0, 0, 0};
     unsigned long long hits = 0;
-#if PKT_BLOCK_2X2
-    /* the block's 4 warps own a 2x2 group of tiles (32x16 pixels): their frusta overlap more than those of a 4x1 strip */
     const unsigned groups_x = (unsigned)(tiles_x + 1) >> 1;
-    const int ty = (int)(blockIdx.x / groups_x) * 2 + (warp >> 1), tx = (int)(blockIdx.x % groups_x) * 2 + (warp & 1);
+    const int gy = (int)(blockIdx.x / groups_x), gx = (int)(blockIdx.x % groups_x);
+    const int ty = gy * 2 + (warp >> 1), tx = gx * 2 + (warp & 1);
     if (tx < tiles_x && ty < tiles_y) {
         int32_t *stack = s_stack[warp];
-#else
-    const unsigned tile = blockIdx.x * PKT_WARPS + warp;   /* < 2^31: the launch rejects larger frames */
-    if (tile < (unsigned)tiles_x * (unsigned)tiles_y) {
-        int32_t *stack = s_stack[warp];
-        const int ty = (int)(tile / (unsigned)tiles_x), tx = (int)(tile - (unsigned)ty * (unsigned)tiles_x);
-#endif
         /* ---- this lane's 4 rays: pixel (tx*16 + (k&1)*8 + lane%8, y0 + ty*8 + (k>>1)*4 + lane/8) ---- */
         const int px0 = tx * 16 + (lane & 7), py0 = y0 + ty * PKT_TILE_H + (lane >> 3);
         unsigned valid = 0;
@@ -515,7 +557,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
         __syncwarp();
         while (top > 0) {
             int npop = top < 8 ? top : 8;
-            if (top > PKT_STACK - 96) npop = 1; /* nearly full: plain DFS (growth <= 3 per level) */
+            if (top > dfs_from) npop = 1; /* nearly full: plain DFS, growth <= 3 per level (see sahbvh_packet_dfs_from) */
             const int j = lane >> 2, c = lane & 3;
             const bool active = j < npop;
             int32_t nd = active ? stack[top - 1 - j] : 0;
@@ -549,6 +591,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
             unsigned ord_mask = __reduce_or_sync(full, push ? (1u << order) : 0u);
             if (push) stack[top + __popc(ord_mask & ((1u << order) - 1u))] = ref;
             top += __popc(ord_mask);
+            if (COUNT && (unsigned long long)top > cnt.max_stack) cnt.max_stack = (unsigned long long)top;
             unsigned m = __ballot_sync(full, cand);
             __syncwarp();
             /* ---- candidates: every ray of the tile runs the reference's own tests ---- */
@@ -608,30 +651,40 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                 pkt_best_s = warp_max(w);
             }
         }
-        /* ---- results ---- */
-#pragma unroll kPktUnroll
-        for (int k = 0; k < PKT_K; k++) {
-            if (!(valid & (1u << k))) continue;
-            const int px = px0 + (k & 1) * 8, py = py0 + (k >> 1) * 4;
+    }
+    /* ---- results: the block's 32 x 16 pixels leave through shared memory, one 32-pixel ROW per warp instruction
+     * (128 contiguous bytes of ids, 1 KiB of records), whichever warp traced them -- the ids may be going to another
+     * GPU's frame over NVLink or to pinned host memory over PCIe, where 32-byte segments waste the link. ---- */
+    __syncthreads();
+    const int bx = gx * 32 + lane;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int r = warp * 4 + q;                    /* row of the block */
+        const int py = y0 + gy * 16 + r;
+        if (py >= y1 || bx >= width) continue;
+        /* pixel (lane, r) of the block was ray k of lane l2 of warp w2 (tile layout above) */
+        const int w2 = (r >> 3) * 2 + (lane >> 4);
+        const int k = (((r & 7) >> 2) << 1) | ((lane >> 3) & 1);
+        const int l2 = ((r & 3) << 3) | (lane & 7);
+        const int32_t bp = s_bp[w2][k][l2];
+        const float bt = s_bt[w2][k][l2];
+        const size_t pix = (size_t)(py - y0) * (size_t)width + (size_t)bx;
+        if (ids_mode == SAH_IDS_PRIM) reinterpret_cast<int32_t *>(ids)[pix] = bp;
+        else if (ids_mode == SAH_IDS_TPRIM) ids[pix] = make_float2(bp >= 0 ? bt : 0.0f, __int_as_float(bp));
+        if (RECORDS) {
             SahHit h;
-            const int32_t bp = s_bp[warp][k][lane];
             if (bp >= 0) {
-                SahRay r;
-                r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
-                r.dx = s_ray[warp][k][0][lane]; r.dy = s_ray[warp][k][1][lane]; r.dz = s_ray[warp][k][2][lane];
+                SahRay ray;
+                ray.ox = cam.px; ray.oy = cam.py; ray.oz = cam.pz;
+                ray.dx = s_ray[w2][k][0][l2]; ray.dy = s_ray[w2][k][1][l2]; ray.dz = s_ray[w2][k][2][l2];
                 const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + bp);
-                sah_finish_hit(r, s_bt[warp][k][lane], bp, s.x, s.y, s.z, h);
-                if (COUNT) hits++;
+                sah_finish_hit(ray, bt, bp, s.x, s.y, s.z, h);
             } else {
                 sah_miss(h);
             }
-            const size_t pix = (size_t)(py - y0) * (size_t)width + (size_t)px;
-            store_hit(out + pix, h);
-            if (ids) {
-                if (ids_prim_only) reinterpret_cast<int32_t *>(ids)[pix] = h.prim;
-                else ids[pix] = make_float2(h.t, __int_as_float(h.prim));
-            }
+            store_hit256(out + pix, h);
         }
+        if (COUNT) hits += (bp >= 0);
     }
     if (COUNT) flush_counters(cnt, hits, counters);
 }
@@ -758,6 +811,14 @@ __global__ void __launch_bounds__(256) k_count_prims(const gpu_hit *__restrict__
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
+__global__ void __launch_bounds__(256) k_count_prim_ids(const int32_t *__restrict__ prims, long long n, unsigned long long *count)
+{
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) c += prims[i] >= 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* handle                                                                                       */
 /* ------------------------------------------------------------------------------------------ */
@@ -814,12 +875,13 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
     b->n_special = wb.n_special;
     b->info.n_wide = wb.n_wide;
     const size_t wide_bytes = (size_t)wb.n_wide * 64, special_bytes = (size_t)(wb.n_special > 0 ? wb.n_special : 1) * 32;
-    size_t node_bytes = (size_t)f->info.n_inner * 64;
+    const bool keep_binary = g_keep_binary.load() != 0;
+    size_t node_bytes = keep_binary ? (size_t)f->info.n_inner * 64 : 0;
     size_t sph_bytes = ((size_t)f->info.n_spheres + 1) * 16;
     size_t col_bytes = ((size_t)f->info.n_spheres + 1) * 4;
     cudaError_t err = cudaSuccess;
     do {
-        if ((err = cudaMalloc(&b->d_nodes, node_bytes)) != cudaSuccess) break;
+        if (keep_binary && (err = cudaMalloc(&b->d_nodes, node_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_spheres4, sph_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_colors, col_bytes)) != cudaSuccess) break;
         if ((err = cudaMalloc(&b->d_counters, 72 * sizeof(unsigned long long))) != cudaSuccess) break;
@@ -829,7 +891,7 @@ extern "C" int gpu_bvh_from_flat(const flat_bvh *f, int device, gpu_bvh **out)
         if ((err = cudaMemcpy(b->d_wide_full, wb.full, wide_bytes * 2, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_wide, wb.nodes, wide_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_special, wb.special, special_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        if ((err = cudaMemcpy(b->d_nodes, f->nodes, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (keep_binary && (err = cudaMemcpy(b->d_nodes, f->nodes, node_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_spheres4, f->spheres4, sph_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaMemcpy(b->d_colors, f->colors, col_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
         if ((err = cudaStreamCreateWithFlags(&b->streams[0], cudaStreamNonBlocking)) != cudaSuccess) break;
@@ -863,6 +925,12 @@ static int gpu_bvh_from_parts(gpu_bvh_parts *p, int device, gpu_bvh **out)
     b->info = p->info;
     b->info.device = device;
     b->d_nodes = p->d_nodes; b->d_spheres4 = p->d_spheres4; b->d_colors = p->d_colors;
+    if (b->d_nodes && g_keep_binary.load() == 0) {
+        /* the binary tree was the collapse's input; the default kernels never read it */
+        cudaFree(b->d_nodes);
+        b->d_nodes = nullptr;
+        b->info.device_bytes -= (int64_t)b->info.n_inner * 64;
+    }
     b->d_wide = p->d_wide; b->d_wide_full = p->d_wide_full; b->d_special = p->d_special;
     b->n_wide = p->n_wide; b->n_special = p->n_special;
     memset(p, 0, sizeof *p);
@@ -891,7 +959,7 @@ extern "C" int64_t gpu_bvh_download(const gpu_bvh *b, int what, void *out, int64
     const void *src = nullptr;
     int64_t bytes = 0;
     switch (what) {
-    case 0: src = b->d_nodes; bytes = (int64_t)b->info.n_inner * 64; break;
+    case 0: src = b->d_nodes; bytes = b->d_nodes ? (int64_t)b->info.n_inner * 64 : 0; break;
     case 1: src = b->d_spheres4; bytes = ((int64_t)b->info.n_spheres + 1) * 16; break;
     case 2: src = b->d_colors; bytes = ((int64_t)b->info.n_spheres + 1) * 4; break;
     case 3: src = b->d_wide; bytes = (int64_t)b->n_wide * 64; break;
@@ -1045,9 +1113,13 @@ static int trace_grid(const gpu_bvh *b, long long n)
     return (int)blocks;
 }
 
-int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count)
+int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out, cudaStream_t st, bool count, void *d_prims)
 {
     if (n == 0) return SAHBVH_OK;
+    if (!d_out && (!d_prims || count || g_ray_mode.load() != SAHBVH_RAYS_WIDE)) {
+        sahbvh_set_error("ray-buffer launch without a record buffer: the 4-byte output needs SAHBVH_RAYS_WIDE");
+        return SAHBVH_E_ARG;
+    }
     const SahScene sc = sahbvh_make_scene(b->info);
     if (g_ray_mode.load() == SAHBVH_RAYS_WIDE) {
         /* persistent grid over the 4-wide tree: every resident warp pulls 128-ray chunks */
@@ -1064,12 +1136,15 @@ int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out,
         CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
         if (count)
             k_trace_rays_wide<true><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->d_spheres4, b->d_special, b->n_special, sc,
-                                                                                 (const float *)d_rays, n, (gpu_hit *)d_out, ctr, b->d_counters);
+                                                                                 (const float *)d_rays, n, (gpu_hit *)d_out, nullptr, ctr, b->d_counters);
         else
             k_trace_rays_wide<false><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->d_spheres4, b->d_special, b->n_special, sc,
-                                                                                  (const float *)d_rays, n, (gpu_hit *)d_out, ctr, nullptr);
+                                                                                  (const float *)d_rays, n, (gpu_hit *)d_out,
+                                                                                  d_out ? nullptr : (int32_t *)d_prims, ctr, nullptr);
     } else if (g_ray_mode.load() == SAHBVH_RAYS_COOP) {
         /* persistent grid: every resident warp pulls 128-ray chunks from a per-launch counter */
+        int brc = sahbvh_need_binary_tree(b);
+        if (brc != SAHBVH_OK) return brc;
         if (b->coop_blocks_per_sm == 0) {
             int nb = 0;
             CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_rays_coop<false>, COOP_WARPS * 32, 0));
@@ -1088,6 +1163,8 @@ int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out,
             k_trace_rays_coop<false><<<(unsigned)blocks, COOP_WARPS * 32, 0, st>>>(b->d_nodes, b->d_spheres4, sc, (const float *)d_rays,
                                                                                   n, (gpu_hit *)d_out, ctr, nullptr);
     } else {
+        int brc = sahbvh_need_binary_tree(b);
+        if (brc != SAHBVH_OK) return brc;
         int grid = trace_grid(b, n);
         if (count)
             k_trace_rays<true><<<grid, TRACE_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc,
@@ -1121,36 +1198,47 @@ void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c)
 }
 
 int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
-                          cudaStream_t st, bool count, void *d_ids, int ids_prim_only)
+                          cudaStream_t st, bool count, void *d_ids, int ids_mode)
 {
     if (y1 <= y0 || width <= 0) return SAHBVH_OK;
+    if (!d_ids) ids_mode = SAH_IDS_NONE;
+    if (!d_out && (ids_mode == SAH_IDS_NONE || count)) {
+        sahbvh_set_error("primary launch without an output buffer");
+        return SAHBVH_E_ARG;
+    }
     SahCamera c;
     sahbvh_make_camera(cam, width, height, &c);
     gpu_hit *out = (gpu_hit *)d_out;
     float2 *ids = (float2 *)d_ids;
     const SahScene sc = sahbvh_make_scene(b->info);
     if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
-        long long tiles = (long long)((width + 15) / 16) * ((y1 - y0 + PKT_TILE_H - 1) / PKT_TILE_H);
-        if (tiles >= (1ll << 31) - PKT_WARPS) {
-            sahbvh_set_error("frame too large for one launch (%lld tiles): trace it in row bands", tiles);
+        /* one CTA per 32 x 16 pixel group (2 x 2 tiles of 16 x 8) */
+        const long long groups = (long long)((width + 31) / 32) * ((y1 - y0 + 2 * PKT_TILE_H - 1) / (2 * PKT_TILE_H));
+        if (groups >= (1ll << 31) - 1) {
+            sahbvh_set_error("frame too large for one launch (%lld tile groups): trace it in row bands", groups);
             return SAHBVH_E_ARG;
         }
-        unsigned grid = (unsigned)((tiles + PKT_WARPS - 1) / PKT_WARPS);
-        if (PKT_BLOCK_2X2) grid = (unsigned)(((width + 31) / 32) * ((y1 - y0 + 2 * PKT_TILE_H - 1) / (2 * PKT_TILE_H)));
+        const unsigned grid = (unsigned)groups;
+        const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth);
         if (count)
-            k_trace_primary_packet<true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
-                                                                         out, ids, ids_prim_only, b->d_counters);
+            k_trace_primary_packet<true, true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                                                                               out, ids, ids_mode, dfs_from, b->d_counters);
+        else if (out)
+            k_trace_primary_packet<false, true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                                                                                out, ids, ids_mode, dfs_from, nullptr);
         else
-            k_trace_primary_packet<false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
-                                                                          out, ids, ids_prim_only, nullptr);
+            k_trace_primary_packet<false, false><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                                                                                 nullptr, ids, ids_mode, dfs_from, nullptr);
     } else {
+        int rc = sahbvh_need_binary_tree(b);
+        if (rc != SAHBVH_OK) return rc;
         dim3 grid((width + 31) / 32, (y1 - y0 + 7) / 8);
         if (count)
             k_trace_primary<true><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
-                                                                   out, ids, ids_prim_only, b->d_counters);
+                                                                   out, ids, ids_mode, b->d_counters);
         else
             k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
-                                                                    out, ids, ids_prim_only, nullptr);
+                                                                    out, ids, ids_mode, nullptr);
     }
     g_launches++;
     CU_TRY(cudaGetLastError());
@@ -1211,7 +1299,7 @@ extern "C" int gpu_trace_closest_hit_dev(gpu_bvh *b, const void *d_rays, int64_t
     return sahbvh_launch_rays(b, d_rays, n, d_out, (cudaStream_t)stream, false);
 }
 
-extern "C" int gpu_trace_closest_hit(gpu_bvh *b, const Ray *rays, int64_t n, gpu_hit *out)
+static int trace_rays_host(gpu_bvh *b, const Ray *rays, int64_t n, void *out, bool prims_only)
 {
     if (!b || n < 0 || (n > 0 && (!rays || !out))) {
         sahbvh_set_error("gpu_trace_closest_hit: bad arguments");
@@ -1219,22 +1307,44 @@ extern "C" int gpu_trace_closest_hit(gpu_bvh *b, const Ray *rays, int64_t n, gpu
     }
     if (n == 0) return SAHBVH_OK;
     DeviceGuard guard(b->device);
+    const size_t rec = prims_only ? sizeof(int32_t) : sizeof(gpu_hit);
     long long chunk = n < host_chunk_rays() ? n : host_chunk_rays();
-    int rc = ensure_staging(b, (size_t)chunk * sizeof(Ray), (size_t)chunk * sizeof(gpu_hit));
+    int rc = ensure_staging(b, (size_t)chunk * sizeof(Ray), (size_t)chunk * rec);
     if (rc != SAHBVH_OK) return rc;
     int k = 0;
     for (long long off = 0; off < n; off += chunk, k ^= 1) {
         long long m = n - off < chunk ? n - off : chunk;
         cudaStream_t st = b->streams[k];
         CU_TRY(cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
-        rc = sahbvh_launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
+        rc = prims_only ? sahbvh_launch_rays(b, b->d_in[k], m, nullptr, st, false, b->d_out[k])
+                        : sahbvh_launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
         if (rc != SAHBVH_OK) return rc;
-        CU_TRY(cudaMemcpyAsync(out + off, b->d_out[k], (size_t)m * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync((char *)out + (size_t)off * rec, b->d_out[k], (size_t)m * rec, cudaMemcpyDeviceToHost, st));
         /* the staging pair k is reused two chunks later: the stream orders it */
     }
     CU_TRY(cudaStreamSynchronize(b->streams[0]));
     CU_TRY(cudaStreamSynchronize(b->streams[1]));
     return SAHBVH_OK;
+}
+
+extern "C" int gpu_trace_closest_hit(gpu_bvh *b, const Ray *rays, int64_t n, gpu_hit *out)
+{
+    return trace_rays_host(b, rays, n, out, false);
+}
+
+extern "C" int gpu_trace_closest_hit_prims(gpu_bvh *b, const Ray *rays, int64_t n, int32_t *prims)
+{
+    return trace_rays_host(b, rays, n, prims, true);
+}
+
+extern "C" int gpu_trace_closest_hit_dev_prims(gpu_bvh *b, const void *d_rays, int64_t n, void *d_prims, void *stream)
+{
+    if (!b || n < 0 || (n > 0 && (!d_rays || !d_prims))) {
+        sahbvh_set_error("gpu_trace_closest_hit_dev_prims: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    DeviceGuard guard(b->device);
+    return sahbvh_launch_rays(b, d_rays, n, nullptr, (cudaStream_t)stream, false, d_prims);
 }
 
 extern "C" int gpu_trace_primary_dev(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
@@ -1249,19 +1359,19 @@ extern "C" int gpu_trace_primary_dev(gpu_bvh *b, const Camera *cam, int width, i
 extern "C" int gpu_trace_primary_dev_ids(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
                                          void *d_out, void *d_ids, void *stream)
 {
-    int rc = check_frame(b, cam, width, height, y0, y1, d_out);
+    int rc = check_frame(b, cam, width, height, y0, y1, d_out ? d_out : d_ids);
     if (rc != SAHBVH_OK) return rc;
     DeviceGuard guard(b->device);
-    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_ids, 0);
+    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_ids, SAH_IDS_TPRIM);
 }
 
 extern "C" int gpu_trace_primary_dev_prims(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
                                            void *d_out, void *d_prims, void *stream)
 {
-    int rc = check_frame(b, cam, width, height, y0, y1, d_out);
+    int rc = check_frame(b, cam, width, height, y0, y1, d_out ? d_out : d_prims);
     if (rc != SAHBVH_OK) return rc;
     DeviceGuard guard(b->device);
-    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_prims, 1);
+    return sahbvh_launch_primary(b, cam, width, height, y0, y1, d_out, (cudaStream_t)stream, false, d_prims, SAH_IDS_PRIM);
 }
 
 /* prim ids of image rows -> full hit records: t, point and normal are pure functions of the pixel's ray and the
@@ -1310,26 +1420,130 @@ extern "C" int gpu_hits_from_prims_dev(gpu_bvh *b, const Camera *cam, int width,
     return SAHBVH_OK;
 }
 
-extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out)
+/* ---- host-buffer frames.  fmt: what goes back over PCIe per pixel ---- */
+
+static long long env_ll(const char *name, long long dflt, long long lo)
+{
+    const char *e = getenv(name);
+    if (!e) return dflt;
+    const long long v = atoll(e);
+    return v < lo ? dflt : v;
+}
+
+/* SAHBVH_HOST_DIRECT (tuning aid): 1 = when the caller's buffer is page-locked, the kernel stores its rows straight
+ * into it through the host mapping (no staging buffer, no copy engine); 0 = staged bands + cudaMemcpyAsync. */
+static int host_direct_mode()
+{
+    static int v = -1;
+    if (v < 0) v = (int)env_ll("SAHBVH_HOST_DIRECT", SAHBVH_HOST_DIRECT_DEFAULT, 0);
+    return v;
+}
+
+/* device-visible alias of a page-locked host buffer, or NULL (pageable memory / no unified addressing) */
+static void *mapped_alias(const void *host_ptr)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
+/* enqueue only: kernels and copies are in flight on the handle's two streams when this returns;
+ * sahbvh_primary_host_wait() blocks until the caller's buffer is complete.  (Split so that one host thread can
+ * drive several devices' bands concurrently, multi_gpu.cu.) */
+int sahbvh_primary_host_enqueue(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *out, int fmt)
 {
     int rc = check_frame(b, cam, width, height, y0, y1, out);
     if (rc != SAHBVH_OK) return rc;
     if (y1 == y0) return SAHBVH_OK;
     DeviceGuard guard(b->device);
-    /* row bands of ~2 Mi pixels so the D2H copy of one band overlaps the next band's kernel */
-    int band = (int)(HOST_CHUNK_RAYS / width);
-    band = band < 8 ? 8 : (band / 8) * 8;
-    if (band > y1 - y0) band = ((y1 - y0 + 7) / 8) * 8;
-    rc = ensure_staging(b, 0, (size_t)band * (size_t)width * sizeof(gpu_hit));
+    const size_t px_bytes = fmt == HOSTFMT_RECORDS ? sizeof(gpu_hit) : fmt == HOSTFMT_PRIMS ? 4 : 8;
+    const int ids_mode = fmt == HOSTFMT_PRIMS ? SAH_IDS_PRIM : fmt == HOSTFMT_TPRIM ? SAH_IDS_TPRIM : SAH_IDS_NONE;
+    if (host_direct_mode() && fmt != HOSTFMT_RECORDS) {
+        void *alias = mapped_alias(out);
+        if (alias) /* one launch for the whole frame; its 128/256-byte row stores are the PCIe writes */
+            return sahbvh_launch_primary(b, cam, width, height, y0, y1, nullptr, b->streams[0], false, alias, ids_mode);
+    }
+    /* row bands, alternating between two streams, so the D2H copy of one band overlaps the next band's kernel:
+     * ~4 Mi pixels per band for 32-byte records (128 MiB), ~1 Mi pixels for the compact formats (4-8 MiB) */
+    const long long band_px = fmt == HOSTFMT_RECORDS ? HOST_CHUNK_RAYS : env_ll("SAHBVH_PRIMARY_BAND_PIXELS", 1ll << 20, 4096);
+    int band = (int)(band_px / width);
+    band = band < 16 ? 16 : (band / 16) * 16;         /* whole 32 x 16 pixel CTA groups */
+    if (band > y1 - y0) band = ((y1 - y0 + 15) / 16) * 16;
+    rc = ensure_staging(b, 0, (size_t)band * (size_t)width * px_bytes);
     if (rc != SAHBVH_OK) return rc;
     int k = 0;
     for (int ya = y0; ya < y1; ya += band, k ^= 1) {
-        int yb = ya + band < y1 ? ya + band : y1;
+        const int yb = ya + band < y1 ? ya + band : y1;
         cudaStream_t st = b->streams[k];
-        rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false, nullptr, 0);
+        if (fmt == HOSTFMT_RECORDS) rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false, nullptr, SAH_IDS_NONE);
+        else rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, nullptr, st, false, b->d_out[k], ids_mode);
         if (rc != SAHBVH_OK) return rc;
-        CU_TRY(cudaMemcpyAsync(out + (size_t)(ya - y0) * (size_t)width, b->d_out[k],
-                               (size_t)(yb - ya) * (size_t)width * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync((char *)out + (size_t)(ya - y0) * (size_t)width * px_bytes, b->d_out[k],
+                               (size_t)(yb - ya) * (size_t)width * px_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    return SAHBVH_OK;
+}
+
+int sahbvh_primary_host_wait(gpu_bvh *b)
+{
+    DeviceGuard guard(b->device);
+    CU_TRY(cudaStreamSynchronize(b->streams[0]));
+    CU_TRY(cudaStreamSynchronize(b->streams[1]));
+    return SAHBVH_OK;
+}
+
+static int trace_primary_host(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *out, int fmt)
+{
+    int rc = sahbvh_primary_host_enqueue(b, cam, width, height, y0, y1, out, fmt);
+    if (rc != SAHBVH_OK || !b || y1 == y0) return rc;
+    return sahbvh_primary_host_wait(b);
+}
+
+extern "C" int gpu_trace_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out)
+{
+    return trace_primary_host(b, cam, width, height, y0, y1, out, HOSTFMT_RECORDS);
+}
+
+extern "C" int gpu_trace_primary_prims(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, int32_t *prims)
+{
+    return trace_primary_host(b, cam, width, height, y0, y1, prims, HOSTFMT_PRIMS);
+}
+
+extern "C" int gpu_trace_primary_tprim(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, gpu_tprim *out)
+{
+    return trace_primary_host(b, cam, width, height, y0, y1, out, HOSTFMT_TPRIM);
+}
+
+/* host id frame -> host records, on demand (H2D 4 B/pixel, k_hits_from_prims, D2H 32 B/pixel, banded over two streams) */
+extern "C" int gpu_hits_from_prims(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1,
+                                   const int32_t *prims, gpu_hit *out)
+{
+    int rc = check_frame(b, cam, width, height, y0, y1, out);
+    if (rc != SAHBVH_OK) return rc;
+    if (!prims) {
+        sahbvh_set_error("gpu_hits_from_prims: NULL prims");
+        return SAHBVH_E_ARG;
+    }
+    if (y1 == y0) return SAHBVH_OK;
+    DeviceGuard guard(b->device);
+    int band = (int)(HOST_CHUNK_RAYS / width);
+    band = band < 1 ? 1 : band;
+    if (band > y1 - y0) band = y1 - y0;
+    rc = ensure_staging(b, (size_t)band * (size_t)width * 4, (size_t)band * (size_t)width * sizeof(gpu_hit));
+    if (rc != SAHBVH_OK) return rc;
+    int k = 0;
+    for (int ya = y0; ya < y1; ya += band, k ^= 1) {
+        const int yb = ya + band < y1 ? ya + band : y1;
+        const size_t off = (size_t)(ya - y0) * (size_t)width, npx = (size_t)(yb - ya) * (size_t)width;
+        cudaStream_t st = b->streams[k];
+        CU_TRY(cudaMemcpyAsync(b->d_in[k], prims + off, npx * 4, cudaMemcpyHostToDevice, st));
+        rc = gpu_hits_from_prims_dev(b, cam, width, height, ya, yb, b->d_in[k], b->d_out[k], st);
+        if (rc != SAHBVH_OK) return rc;
+        CU_TRY(cudaMemcpyAsync(out + off, b->d_out[k], npx * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaStreamSynchronize(b->streams[0]));
     CU_TRY(cudaStreamSynchronize(b->streams[1]));
@@ -1444,11 +1658,15 @@ extern "C" int gpu_benchmark_with_bvh(gpu_bvh *b, const Ray *rays, int64_t n, in
         long long m = n - off < chunk ? n - off : chunk;
         cudaStream_t st = b->streams[k];
         CU_TRY(cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
-        rc = sahbvh_launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
+        /* benchmark.c:242-244 only counts hit_something: the 4-wide kernel writes 4-byte ids, no records */
+        const bool ids_only = g_ray_mode.load() == SAHBVH_RAYS_WIDE;
+        rc = ids_only ? sahbvh_launch_rays(b, b->d_in[k], m, nullptr, st, false, b->d_out[k])
+                      : sahbvh_launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
         if (rc != SAHBVH_OK) return rc;
         int cblocks = (int)((m + 255) / 256);
         if (cblocks > b->sm_count * 8) cblocks = b->sm_count * 8;
-        k_count_prims<<<cblocks, 256, 0, st>>>((const gpu_hit *)b->d_out[k], m, cnt);
+        if (ids_only) k_count_prim_ids<<<cblocks, 256, 0, st>>>((const int32_t *)b->d_out[k], m, cnt);
+        else k_count_prims<<<cblocks, 256, 0, st>>>((const gpu_hit *)b->d_out[k], m, cnt);
         g_launches++;
         CU_TRY(cudaGetLastError());
     }
@@ -1567,6 +1785,61 @@ extern "C" int sahbvh_peer_signal(void *d_flag, uint64_t value, void *stream)
         return SAHBVH_E_ARG;
     }
     k_peer_signal<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long *)d_flag, (unsigned long long)value);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return SAHBVH_OK;
+}
+
+/* Device-side wait: the stream does not advance until every one of the n 64-bit flags is >= value (flags written by
+ * other GPUs' sahbvh_peer_signal through peer memory, or read from another GPU's memory through a mapping).  This
+ * is the frame loop's back-pressure: the owner of a frame buffer consumes frame k only when every band has landed,
+ * and a producer reuses a buffer only when the owner has signalled that it was consumed -- without a host round trip.
+ * A flag that never arrives would hang the stream, so the wait gives up after timeout_ms and stores 1 into *status
+ * (a 32-bit word, may be NULL) instead. */
+__global__ void k_peer_wait(const unsigned long long *flags, int n, unsigned long long value, unsigned long long timeout_ns,
+                            unsigned int *status)
+{
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int i = 0; i < n; i++) {
+        const volatile unsigned long long *f = flags + i;
+        while (*f < value) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) {
+                if (status) *status = 1u;
+                return;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+extern "C" int sahbvh_peer_wait(const void *d_flags, int n, uint64_t value, uint32_t timeout_ms, void *d_status, void *stream)
+{
+    if (!d_flags || n <= 0) {
+        sahbvh_set_error("sahbvh_peer_wait: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    k_peer_wait<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned long long *)d_flags, n, (unsigned long long)value,
+                                                   (unsigned long long)(timeout_ms ? timeout_ms : 2000u) * 1000000ull,
+                                                   (unsigned int *)d_status);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return SAHBVH_OK;
+}
+
+/* benchmark.c:242-244 on an id buffer already on the device: *d_count (uint64) += number of ids >= 0 */
+extern "C" int gpu_count_prims_dev(const void *d_prims, int64_t n, void *d_count, void *stream)
+{
+    if (!d_prims || !d_count || n < 0) {
+        sahbvh_set_error("gpu_count_prims_dev: bad arguments");
+        return SAHBVH_E_ARG;
+    }
+    if (n == 0) return SAHBVH_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_count_prim_ids<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const int32_t *)d_prims, n, (unsigned long long *)d_count);
     g_launches++;
     CU_TRY(cudaGetLastError());
     return SAHBVH_OK;
@@ -1754,9 +2027,38 @@ extern "C" int sahbvh_measure_peaks(int device, sahbvh_peaks *out)
 
 struct ScalarEntry {
     const BVHNode *root;
+    uint64_t fingerprint;
     const Sphere *base;
     gpu_bvh *bvh;
 };
+
+/* The cache is keyed by the root's ADDRESS, and only this library's own free_bvh drops an entry.  A driver that
+ * frees the tree with its own free_bvh (benchmark.c:81-88 wins at link time when src/benchmark.c stays in the
+ * build) and rebuilds can get the same address back from malloc for a different tree.  Every call therefore
+ * re-checks a fingerprint of the top of the tree -- the first 64 nodes in breadth-first order: bounds, child and
+ * sphere pointers, sphere_count (FNV-1a) -- and re-uploads on a mismatch. */
+static uint64_t scalar_fingerprint(const BVHNode *root)
+{
+    const BVHNode *queue[64];
+    int head = 0, tail = 0;
+    queue[tail++] = root;
+    uint64_t h = 1469598103934665603ull;
+    while (head < tail) {
+        const BVHNode *p = queue[head++];
+        unsigned char rec[sizeof(AABB) + 3 * sizeof(void *) + sizeof(int)];
+        memcpy(rec, &p->bounds, sizeof(AABB));
+        memcpy(rec + sizeof(AABB), &p->left, sizeof(void *));
+        memcpy(rec + sizeof(AABB) + sizeof(void *), &p->right, sizeof(void *));
+        memcpy(rec + sizeof(AABB) + 2 * sizeof(void *), &p->sphere, sizeof(void *));
+        memcpy(rec + sizeof(AABB) + 3 * sizeof(void *), &p->sphere_count, sizeof(int));
+        for (size_t i = 0; i < sizeof rec; i++) h = (h ^ rec[i]) * 1099511628211ull;
+        if (!p->sphere && p->left && p->right) {
+            if (tail < 64) queue[tail++] = p->left;
+            if (tail < 64) queue[tail++] = p->right;
+        }
+    }
+    return h;
+}
 static std::mutex g_scalar_mu;
 static std::vector<ScalarEntry> g_scalar;
 
@@ -1803,9 +2105,18 @@ extern "C" int sahbvh_scalar_trace(const BVHNode *root, const Ray *ray, HitRecor
         return SAHBVH_E_ARG;
     }
     std::lock_guard<std::mutex> lock(g_scalar_mu);
+    const uint64_t fp = scalar_fingerprint(root);
     ScalarEntry *e = nullptr;
-    for (auto &s : g_scalar)
-        if (s.root == root) e = &s;
+    for (size_t i = 0; i < g_scalar.size(); i++) {
+        if (g_scalar[i].root != root) continue;
+        if (g_scalar[i].fingerprint == fp) {
+            e = &g_scalar[i];
+        } else { /* same address, different tree: the old one was freed behind our back */
+            gpu_bvh_free(g_scalar[i].bvh);
+            g_scalar.erase(g_scalar.begin() + (long)i);
+        }
+        break;
+    }
     if (!e) {
         const Sphere *base = nullptr;
         int n = 0;
@@ -1829,7 +2140,7 @@ extern "C" int sahbvh_scalar_trace(const BVHNode *root, const Ray *ray, HitRecor
         flat_bvh_release(&f);
         sah_tree_free(&t);
         if (rc != SAHBVH_OK) return rc;
-        g_scalar.push_back({root, base, bvh});
+        g_scalar.push_back({root, fp, base, bvh});
         e = &g_scalar.back();
     }
     gpu_hit h;

@@ -36,7 +36,11 @@ typedef struct gpu_hit {
 } gpu_hit;
 SAHBVH_STATIC_ASSERT(sizeof(gpu_hit) == 32, "gpu_hit layout");
 
-typedef struct gpu_bvh gpu_bvh; /* opaque: flattened tree + SoA spheres resident on ONE device */
+/* opaque: flattened tree + SoA spheres resident on ONE device.  A handle is NOT thread-safe: it owns per-launch
+ * ray cursors, counters and staging buffers, so at most one host thread may be inside a call on a given handle
+ * at a time, and the asynchronous *_dev calls must be issued in order from one thread (use one handle per thread
+ * or per device -- gpu_bvh_replicate -- for concurrency).  Different handles are independent. */
+typedef struct gpu_bvh gpu_bvh;
 
 typedef struct gpu_bvh_info {
     int32_t device;
@@ -110,11 +114,31 @@ int gpu_bvh_get_info(const gpu_bvh *bvh, gpu_bvh_info *info);
 int gpu_trace_closest_hit(gpu_bvh *bvh, const Ray *rays, int64_t n, gpu_hit *out);
 /* Same with DEVICE buffers on `stream` (a cudaStream_t, NULL = default); asynchronous. */
 int gpu_trace_closest_hit_dev(gpu_bvh *bvh, const void *d_rays, int64_t n, void *d_out, void *stream);
+/* Compact output: only `hit.object - spheres` (hit.h:13) per ray, 4 bytes instead of 32 (-1 = miss).  The other
+ * HitRecord fields are pure functions of the ray and that sphere: sahbvh_hit_from_prim (sahbvh_ref_api.h) derives
+ * them on the host for the rays that need them, bit for bit.  Over PCIe this moves 24 + 4 bytes per ray, not 24 + 32. */
+int gpu_trace_closest_hit_prims(gpu_bvh *bvh, const Ray *rays, int64_t n, int32_t *prims);
+int gpu_trace_closest_hit_dev_prims(gpu_bvh *bvh, const void *d_rays, int64_t n, void *d_prims, void *stream);
 
 /* Fused ray generation + closest hit for image rows [y0,y1) of a width x height frame:
  * pixel (x,y) -> u=((float)x/W-0.5f)*aspect, v=(float)y/H-0.5f, get_camera_ray(cam,u,-v)
  * (main.c:356-365 + ray.c:17-32, bit-exact), hit written at out[(y-y0)*width + x]. */
 int gpu_trace_primary(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, gpu_hit *out);
+/* The same frame with compact per-pixel output into a HOST buffer -- what renderer.c:29-58 / benchmark.c:242-244
+ * actually consume is the hit OBJECT (hit.h:13): 4 bytes per pixel (`prims`: post-build sphere index, -1 = miss)
+ * or 8 bytes ({t, prim}).  PCIe carries 4 or 8 bytes per ray instead of 32; the remaining HitRecord fields are
+ * derived on demand, bit-identical to the traced record:
+ *   one pixel, on the host : sahbvh_hit_from_prim(sahbvh_pixel_ray(cam, W, H, x, y), spheres, prim)
+ *   a whole frame          : gpu_hits_from_prims (host buffers) / gpu_hits_from_prims_dev (device buffers)
+ * Page-locked output buffers (sahbvh_host_alloc / sahbvh_host_pin) run at PCIe speed. */
+typedef struct gpu_tprim {
+    float t;
+    int32_t prim;
+} gpu_tprim;
+int gpu_trace_primary_prims(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, int32_t *prims);
+int gpu_trace_primary_tprim(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1, gpu_tprim *out);
+int gpu_hits_from_prims(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
+                        const int32_t *prims, gpu_hit *out);
 int gpu_trace_primary_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
                           void *d_out, void *stream);
 /* Same, and additionally writes the compact 8-byte "ID buffer" record {float t, int32 prim} per pixel
@@ -127,6 +151,7 @@ int gpu_trace_primary_dev_ids(gpu_bvh *bvh, const Camera *cam, int width, int he
  * are pure functions of the pixel's ray and the hit sphere, so gpu_hits_from_prims_dev rebuilds the full,
  * bit-identical 32-byte records from the ids on whichever GPU needs them: the multi-GPU frame assembly
  * gathers 4 bytes per pixel over NVLink instead of 32. */
+/* d_out may be NULL in both *_dev_ids and *_dev_prims: then no 32-byte records are written (or computed) at all. */
 int gpu_trace_primary_dev_prims(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
                                 void *d_out, void *d_prims, void *stream);
 int gpu_hits_from_prims_dev(gpu_bvh *bvh, const Camera *cam, int width, int height, int y0, int y1,
@@ -144,6 +169,13 @@ int sahbvh_peer_open(int device, const sahbvh_ipc_handle *handle, void **d_ptr);
  * the store); the root reads the slots when it wants to consume a frame.  No collective runs in the frame loop. */
 int sahbvh_peer_signal(void *d_flag, uint64_t value, void *stream);
 int sahbvh_peer_read_flags(const void *d_flags, int n, uint64_t *out, void *stream);
+/* Device-side wait (no host round trip): `stream` does not advance until all n 64-bit flags at d_flags are >= value.
+ * With sahbvh_peer_signal this is the frame loop's back-pressure -- the owner consumes frame k once every band's
+ * flag says k, a producer reuses a frame buffer once the owner's "consumed" flag allows it.  Gives up after
+ * timeout_ms (0 = 2000) and stores 1 into the 32-bit word *d_status (may be NULL) instead of hanging the stream. */
+int sahbvh_peer_wait(const void *d_flags, int n, uint64_t value, uint32_t timeout_ms, void *d_status, void *stream);
+/* benchmark.c:242-244 over an id buffer that is already on the device: *d_count (uint64) += #(ids >= 0).  Asynchronous. */
+int gpu_count_prims_dev(const void *d_prims, int64_t n, void *d_count, void *stream);
 int sahbvh_peer_close(int device, void *d_ptr);   /* for pointers from sahbvh_peer_open */
 int sahbvh_peer_free(int device, void *d_ptr);    /* for pointers from sahbvh_peer_alloc */
 /* Page-locked host buffers for the host-pointer entry points (gpu_trace_closest_hit, gpu_trace_primary, ...):
@@ -170,6 +202,10 @@ int sahbvh_set_primary_mode(int mode);
 #define SAHBVH_RAYS_COOP 1
 #define SAHBVH_RAYS_WIDE 2
 int sahbvh_set_ray_mode(int mode);
+/* The 64-byte binary tree is read only by SAHBVH_PRIMARY_PER_RAY, SAHBVH_RAYS_COOP and SAHBVH_RAYS_ONE_SHOT.
+ * Handles created while keep == 0 (the default) do not hold it (64 MB per million spheres); those modes then
+ * return SAHBVH_E_ARG on such a handle.  Set keep = 1 BEFORE gpu_bvh_upload / gpu_bvh_build to use them. */
+int sahbvh_set_keep_binary_tree(int keep);
 /* Ray generation only (parity aid for ray.c): writes Ray records for rows [y0,y1). */
 int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out, int device);
 
@@ -205,6 +241,42 @@ int gpu_accumulate(float *accum, int frames, const uint8_t *rgba, int64_t n_pixe
 int gpu_accumulate_dev(void *d_accum, int frames, const void *d_rgba, int64_t n_pixels, void *d_avg_rgba, void *stream);
 /* Binary PPM (P6) of an RGBA8 frame, in place of SDL_RenderDrawPoint (main.c:376,402). 0 = ok. */
 int sahbvh_write_ppm(const char *path, const uint8_t *rgba, int width, int height);
+
+/* ---- one process, N devices (multi_gpu.cu).  The reference's drivers are single loops over pixels (main.c:356-366)
+ * and rays (benchmark.c:230-245); rays are independent and the tree is read-only, so the loop shards: the BVH is
+ * replicated on every device and each device takes a contiguous band of rows / range of rays.  No collective: the
+ * bands' own stores assemble the frame, in the caller's host buffer or in one device's memory (peer stores). ---- */
+typedef struct gpu_bvh_set gpu_bvh_set; /* N replicas of one tree, one worker thread per device; NOT thread-safe */
+/* Device-to-device copies of src's flattened arrays (NVLink between peers; nothing is rebuilt).  devices == NULL
+ * means ordinals 0 .. n_devices-1; an ordinal may repeat (several bands on one device).  src stays valid and
+ * independent.  devices[0] is the set's ROOT: the device that owns an assembled frame (gpu_trace_primary_prims_multi_dev). */
+int gpu_bvh_replicate(const gpu_bvh *src, const int *devices, int n_devices, gpu_bvh_set **out);
+/* gpu_bvh_build on devices[0], then gpu_bvh_replicate: build_bvh_node's contract (spheres permuted in place). */
+int gpu_bvh_build_replicated(Sphere *spheres, int n_total, int start, int end, int depth,
+                             const int *devices, int n_devices, gpu_bvh_set **out);
+void gpu_bvh_set_free(gpu_bvh_set *set);
+int gpu_bvh_set_size(const gpu_bvh_set *set);
+gpu_bvh *gpu_bvh_set_get(gpu_bvh_set *set, int i);   /* borrowed: the set keeps ownership */
+/* the sharding rules: contiguous ray ranges; row bands of whole 16-row blocks (last band takes the remainder) */
+void sahbvh_shard_range(int64_t n, int part, int n_parts, int64_t *lo, int64_t *hi);
+void sahbvh_shard_rows(int height, int part, int n_parts, int *y0, int *y1);
+/* main.c:356-366 over N devices: the whole width x height frame into a HOST buffer (32-byte records / 4-byte ids). */
+int gpu_trace_primary_multi(gpu_bvh_set *set, const Camera *cam, int width, int height, gpu_hit *out);
+int gpu_trace_primary_prims_multi(gpu_bvh_set *set, const Camera *cam, int width, int height, int32_t *prims);
+/* The id frame assembled in the ROOT device's memory: every device's trace kernel stores its band's rows into
+ * d_prims (memory of devices[0]) through peer access, over NVLink, while it computes.  Asynchronous; root_stream (a
+ * stream of the root device, NULL = its default stream) is made to wait for every band's completion event, so
+ * whatever is enqueued on it afterwards (gpu_hits_from_prims_dev, gpu_count_prims_dev, a copy) sees the whole frame. */
+int gpu_trace_primary_prims_multi_dev(gpu_bvh_set *set, const Camera *cam, int width, int height, void *d_prims,
+                                      void *root_stream);
+/* benchmark.c:230-245 over N devices: contiguous ray ranges, host buffers. */
+int gpu_trace_closest_hit_multi(gpu_bvh_set *set, const Ray *rays, int64_t n, gpu_hit *out);
+int gpu_trace_closest_hit_prims_multi(gpu_bvh_set *set, const Ray *rays, int64_t n, int32_t *prims);
+int gpu_benchmark_with_bvh_multi(gpu_bvh_set *set, const Ray *rays, int64_t n, int64_t *intersections);
+/* gpu_render_frame per row band; the counter-based draws are keyed by the pixel's index in the whole frame, so the
+ * frame does not depend on the number of devices.  samples (may be NULL): [pixel of the frame][max_depth]. */
+int gpu_render_frame_multi(gpu_bvh_set *set, const Camera *cam, int width, int height, int max_depth, uint64_t seed,
+                           const Vec3 *samples, uint8_t *rgba_out);
 
 /* Instrumented trace (counts work per ray; slower; same hits). */
 int gpu_trace_closest_hit_stats(gpu_bvh *bvh, const void *d_rays, int64_t n, void *d_out, gpu_trace_stats *stats);

@@ -46,6 +46,10 @@ BVHNode *build_bvh_node(Sphere *spheres, int start, int end, int depth);
 /* benchmark.c:81-88 (declared in include/Custom/benchmark.h:7).  Also drops the GPU copy
  * that ray_bvh_intersect() cached for this root. */
 void free_bvh(BVHNode *node);
+/* Drops the GPU copy ray_bvh_intersect() cached for `root` without freeing the tree: for drivers that keep their
+ * own free_bvh (benchmark.c:81-88) -- call it first.  (A stale entry is also detected by a fingerprint of the top
+ * of the tree on the next call, so forgetting this costs one re-upload, not wrong hits.) */
+void sahbvh_scalar_forget(const BVHNode *root);
 
 /* ---- intersection (include/Custom/hit.h:16-18, src/hit.c) ------------------------------ */
 
@@ -67,6 +71,12 @@ Ray get_camera_ray(Camera *camera, float u, float v);
 Ray get_camera_ray_wh(const Camera *camera, float u, float v, int width, int height);
 /* camera.c:10-18 */
 void camera_update(Camera *camera);
+/* main.c:362-365: the primary ray of pixel (x, y) of a width x height frame (u, v, flipped v, get_camera_ray). */
+Ray sahbvh_pixel_ray(const Camera *cam, int width, int height, int x, int y);
+/* hit.h:8-14 on demand: the record ray_bvh_intersect returned for `ray`, rebuilt from the index of the sphere it
+ * hit (gpu_trace_primary_prims / gpu_trace_closest_hit_prims return 4 bytes per ray); prim < 0 = the all-zero
+ * miss record.  Pure host arithmetic (ray_sphere_intersect on the winner), bit-identical to the traced record. */
+HitRecord sahbvh_hit_from_prim(Ray ray, Sphere *spheres, int32_t prim);
 
 /* ---- primitives / samplers (include/Custom/sphere.h:14-19, src/sphere.c) --------------- */
 

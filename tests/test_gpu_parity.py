@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 def gpu(pkg):
     if pkg.device_count() < 1:
         pytest.fail("no CUDA device: the closest-hit path has no CPU fallback")
+    pkg.set_keep_binary_tree(True)   # this module switches to the binary-tree kernels on its handles (tests/test_gpu_round2.py runs the default)
     return pkg
 
 

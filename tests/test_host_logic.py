@@ -327,6 +327,38 @@ def test_scalar_primitives_match_oracle(pkg, oracle):
     assert agree > 100
 
 
+def test_lazy_hit_record_from_primitive_id(pkg, oracle):
+    """hit.h:8-14 on demand: sahbvh_pixel_ray == main.c:362-365 + ray.c:17-32 for any W x H, and
+    sahbvh_hit_from_prim(ray, spheres, prim) == the record the traversal returned for that ray (host arithmetic)."""
+    oracle.srand(7)
+    s = oracle.scene_random(20)
+    nodes = oracle.build(s, 0, 20, 0)
+    cam = oracle.default_camera()
+    for W, H in ((800, 600), (333, 97)):
+        rays = oracle.primary_rays(cam, W, H)
+        want, _ = oracle.trace_bvh(nodes, s, 20, rays)
+        rng = np.random.default_rng(W)
+        picks = list(rng.integers(0, W * H, 200)) + list(np.nonzero(want["prim"] >= 0)[0][:200])
+        nhit = 0
+        for p in picks:
+            x, y = int(p % W), int(p // W)
+            pkg.lib.sahbvh_pixel_ray.restype = pkg._Ray
+            pkg.lib.sahbvh_pixel_ray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+            r = pkg.lib.sahbvh_pixel_ray(cam.ctypes.data, W, H, x, y)
+            got_ray = np.array([r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z], np.float32)
+            assert got_ray.tobytes() == rays[p].tobytes()
+            rec = pkg.hit_from_prim(cam, W, H, x, y, s, int(want["prim"][p]))
+            assert rec.hit == int(want["prim"][p] >= 0)
+            got = np.array([rec.t, rec.p.x, rec.p.y, rec.p.z, rec.n.x, rec.n.y, rec.n.z], np.float32)
+            assert got.tobytes() == np.array([want["t"][p], *want["p"][p], *want["n"][p]], np.float32).tobytes()
+            if rec.hit:
+                nhit += 1
+                assert rec.obj == s.ctypes.data + 20 * int(want["prim"][p])
+            else:
+                assert rec.obj is None
+        assert nhit >= 100
+
+
 def test_write_ppm(pkg, tmp_path):
     rgba = (np.arange(7 * 5 * 4) % 251).astype(np.uint8).reshape(-1, 4)
     path = str(tmp_path / "frame.ppm")
