@@ -85,6 +85,8 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
 #define HOSTFMT_TPRIM 2   /* {float t, int32 prim}, 8 B */
 int sahbvh_primary_host_enqueue(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *out, int fmt);
 int sahbvh_primary_host_wait(gpu_bvh *b);
+/* staging pairs d_in[0..1] / d_out[0..1] of the host-buffer entry points, grown on demand */
+int sahbvh_ensure_staging(gpu_bvh *b, size_t in_bytes, size_t out_bytes);
 extern "C" int sahbvh_set_packet_dfs_from(int v); /* diagnostic, see sahbvh_kernels.cu */
 /* the 64-byte binary tree is only read by the selectable binary-tree kernels: it is built from the 4-wide twin on
  * first use instead of being kept in every handle */

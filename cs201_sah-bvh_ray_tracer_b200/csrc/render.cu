@@ -306,30 +306,18 @@ extern "C" int gpu_render_frame(gpu_bvh *b, const Camera *cam, int width, int he
         sahbvh_set_error("gpu_render_frame: cudaSetDevice(%d) failed", b->device);
         return SAHBVH_E_CUDA;
     }
-    void *d_samples = nullptr, *d_rgba = nullptr;
-    int rc = SAHBVH_OK;
-    cudaError_t e = cudaMalloc(&d_rgba, (size_t)n_pixels * 4);
-    if (e == cudaSuccess && samples && max_depth > 0) {
-        e = cudaMalloc(&d_samples, (size_t)n_pixels * (size_t)max_depth * sizeof(Vec3));
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(d_samples, samples, (size_t)n_pixels * (size_t)max_depth * sizeof(Vec3), cudaMemcpyHostToDevice, b->streams[0]);
-    }
-    if (e != cudaSuccess) {
-        sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e));
-        rc = SAHBVH_E_CUDA;
-    }
-    if (rc == SAHBVH_OK) rc = gpu_render_frame_dev(b, cam, width, height, y0, y1, max_depth, seed, d_samples, d_rgba, b->streams[0]);
-    if (rc == SAHBVH_OK) {
-        e = cudaMemcpyAsync(rgba_out, d_rgba, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost, b->streams[0]);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(b->streams[0]);
-        if (e != cudaSuccess) {
-            sahbvh_set_error("gpu_render_frame: %s", cu_errstr(e));
-            rc = SAHBVH_E_CUDA;
-        }
-    }
-    cudaFree(d_samples);
-    cudaFree(d_rgba);
-    return rc;
+    /* frame and samples go through the handle's staging buffers (grown on demand, kept between calls): a cudaMalloc /
+     * cudaFree pair per frame costs more than the frame's D2H copy */
+    const size_t sample_bytes = samples && max_depth > 0 ? (size_t)n_pixels * (size_t)max_depth * sizeof(Vec3) : 0;
+    int rc = sahbvh_ensure_staging(b, sample_bytes, (size_t)n_pixels * 4);
+    if (rc != SAHBVH_OK) return rc;
+    void *d_samples = sample_bytes ? b->d_in[0] : nullptr, *d_rgba = b->d_out[0];
+    if (sample_bytes) CU_TRY(cudaMemcpyAsync(d_samples, samples, sample_bytes, cudaMemcpyHostToDevice, b->streams[0]));
+    rc = gpu_render_frame_dev(b, cam, width, height, y0, y1, max_depth, seed, d_samples, d_rgba, b->streams[0]);
+    if (rc != SAHBVH_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(rgba_out, d_rgba, (size_t)n_pixels * 4, cudaMemcpyDeviceToHost, b->streams[0]));
+    CU_TRY(cudaStreamSynchronize(b->streams[0]));
+    return SAHBVH_OK;
 }
 
 extern "C" int gpu_accumulate_dev(void *d_accum, int frames, const void *d_rgba, int64_t n_pixels, void *d_avg_rgba, void *stream)

@@ -204,6 +204,37 @@ SAH_HD bool sah_box_exact(const SahRay &r, float lox, float loy, float loz, floa
     return tmax >= tmin && tmax > SAH_EPSILON;
 }
 
+/* sah_box_exact with a shortcut for the common case (device only; the RESULT is sah_box_exact's, always).
+ * The six rounded subtractions q = plane - o are the reference's own.  Each quotient t = fl(q / d) is then
+ * approximated by a = fl(q * r), r = rcp.approx(d):  |r*d - 1| <= 2^-23, one rounding in a, one in t, so
+ * a / t is in 1 +- 2^-22 whenever a and t are normal numbers.  With N = max_a min(a1,a2), F = min_a max(a1,a2):
+ *     F (1 - 2^-18) >= max(N, 0)   and   F (1 - 2^-18) > EPSILON
+ * imply  tmax >= tmin  and  tmax > EPSILON  for the reference's own t's (the margin is 16x the error bound; values
+ * below EPSILON -- the only place denormals could matter -- never take the shortcut, and a NaN or infinite
+ * product fails both comparisons).  Anything else, including every zero direction component (r = inf), runs the
+ * six true divisions.  A would-be winner's chord through its sphere's box is ~1e3 times wider than the margin, so
+ * about 99 % of the calls stop after 3 MUFU + 6 FMUL instead of six IEEE division sequences. */
+#if defined(__CUDA_ARCH__)
+SAH_HD bool sah_box_exact_fast(const SahRay &r, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    float rx, ry, rz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(r.dx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(r.dy));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(r.dz));
+    const float a1x = F_MUL(F_SUB(lox, r.ox), rx), a2x = F_MUL(F_SUB(hix, r.ox), rx);
+    const float a1y = F_MUL(F_SUB(loy, r.oy), ry), a2y = F_MUL(F_SUB(hiy, r.oy), ry);
+    const float a1z = F_MUL(F_SUB(loz, r.oz), rz), a2z = F_MUL(F_SUB(hiz, r.oz), rz);
+    const float n = fmaxf(fmaxf(fminf(a1x, a2x), fminf(a1y, a2y)), fmaxf(fminf(a1z, a2z), 0.0f));
+    const float f = F_MUL(fminf(fminf(fmaxf(a1x, a2x), fmaxf(a1y, a2y)), fmaxf(a1z, a2z)), 0.999996185302734375f);
+    const bool finite = fabsf(rx) <= 3.0e38f && fabsf(ry) <= 3.0e38f && fabsf(rz) <= 3.0e38f;   /* no zero / denormal direction axis */
+    if (finite && f >= n && f > SAH_EPSILON) return true;
+    return sah_box_exact(r, lox, loy, loz, hix, hiy, hiz);
+}
+#else
+SAH_HD bool sah_box_exact_fast(const SahRay &r, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    return sah_box_exact(r, lox, loy, loz, hix, hiy, hiz);
+}
+#endif
+
 /* the reference's sphere test up to t (hit.c:21-29); returns true and t when accepted */
 SAH_HD bool sah_sphere_t(const SahRay &r, float cx, float cy, float cz, float rad, float &t_out) {
     float ocx = F_SUB(r.ox, cx), ocy = F_SUB(r.oy, cy), ocz = F_SUB(r.oz, cz);
@@ -270,7 +301,7 @@ SAH_HD void sah_leaf(const SahRay &r, const float *__restrict__ spheres4, int n_
     bool better = (best_prim < 0) || (t < best_t) || (t == best_t && idx > best_prim);
     if (!better) return;
     if (COUNT) cnt->exact++;
-    if (!sah_box_exact(r, lox, loy, loz, hix, hiy, hiz)) return;
+    if (!sah_box_exact_fast(r, lox, loy, loz, hix, hiy, hiz)) return;
     best_t = t;
     best_prim = idx;
     best_s = F_FMA(t, SAH_REL_CULL, r.cull_abs);
@@ -438,7 +469,7 @@ SAH_HD void sah_wide_leaf(const SahRay &r, const float *__restrict__ spheres4, c
     const bool better = (best_prim < 0) || (t < best_t) || (t == best_t && idx > best_prim);
     if (!better) return;
     if (COUNT) cnt->exact++;
-    if (!sah_box_exact(r, lox, loy, loz, hix, hiy, hiz)) return;
+    if (!sah_box_exact_fast(r, lox, loy, loz, hix, hiy, hiz)) return;
     best_t = t;
     best_prim = idx;
     best_s = F_FMA(t, SAH_REL_CULL, r.cull_abs);
@@ -669,7 +700,7 @@ SAH_HD void sah_frustum_axis_setup(SahFrustumAxis &A, float o, float dmin, float
     if (dmin >= SAH_TINY_DIR) {
         A.mode = 0; A.ia = F_DIV(1.0f, dmax); A.ib = F_DIV(1.0f, dmin);
     } else if (dmax <= -SAH_TINY_DIR) {
-        A.mode = 1; A.ia = F_DIV(1.0f, dmin); A.ib = F_DIV(1.0f, dmax);
+        A.mode = 1; A.ia = F_DIV(1.0f, dmax); A.ib = F_DIV(1.0f, dmin);   /* ia <= ib in both modes (sah_frustum_axis_simple) */
     } else if (geometric && pad < 3.0e38f) {
         A.mode = 2;
         A.ia = (dmax >= SAH_TINY_DIR) ? F_DIV(1.0f, dmax) : INFINITY;     /* fastest approach from below */
@@ -721,8 +752,15 @@ SAH_HD bool sah_frustum_simple(const SahFrustumAxis &X, const SahFrustumAxis &Y,
 SAH_HD void sah_frustum_axis_simple(const SahFrustumAxis &A, float lo, float hi, float &LB, float &UB) {
     const bool pos = A.mode == 0;
     const float qn = F_SUB(pos ? lo : hi, A.o), qf = F_SUB(pos ? hi : lo, A.o);
+#if defined(SAH_FRUSTUM_SELECT)
+    /* ia <= ib in both modes (mode 0: 1/dmax <= 1/dmin, both positive; mode 1: 1/dmax <= 1/dmin, both negative), and
+     * rounding is monotone, so min(fl(q*ia), fl(q*ib)) = fl(q * (q >= 0 ? ia : ib)) and max(...) = fl(q * (q >= 0 ? ib : ia)) */
+    LB = F_MUL(qn, qn >= 0.0f ? A.ia : A.ib);
+    UB = F_MUL(qf, qf >= 0.0f ? A.ib : A.ia);
+#else
     LB = fminf(F_MUL(qn, A.ia), F_MUL(qn, A.ib));
     UB = fmaxf(F_MUL(qf, A.ia), F_MUL(qf, A.ib));
+#endif
 }
 
 SAH_HD bool sah_frustum_box_simple(const SahFrustumAxis &X, const SahFrustumAxis &Y, const SahFrustumAxis &Z,

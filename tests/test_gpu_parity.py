@@ -838,9 +838,11 @@ def test_bench_line_contract_small_scene(gpu):
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] >= 3 and d["vs_baseline"] is None
     assert abs(d["value"] - d["config"]["rays_per_step"] / d["ms_per_step"] / 1e6) < 1e-6 * d["value"]
     e = d["e2e"]
-    assert e["value"] > 0 and e["unit"] == "Grays/s" and e["d2h_bytes_per_step"] == 32 * d["config"]["rays_per_step"]
-    r = d["roofline"]
+    assert e["value"] > 0 and e["unit"] == "Grays/s" and e["d2h_bytes_per_step"] == 4 * d["config"]["rays_per_step"]
+    assert "pass" in e["api"] and len(d["e2e_variants"]) == 4 and all(v["value"] > 0 for v in d["e2e_variants"])
+    r = d["roofline"]       # no ncu instruction count is on file for this small scene: the line falls back to the HBM fraction
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["kernel_ms"] > 0 and r["kernel_ms_ids_only"] > 0 and 0 < r["hbm_compulsory_frac"] < 1
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert "20000" in d["config"]["workload"] and "l2" in d["config"]
 

@@ -368,11 +368,11 @@ def test_write_ppm(pkg, tmp_path):
     assert data[len(b"P6\n7 5\n255\n"):] == rgba[:, :3].tobytes()
 
 
-def _compile_example(tmp_path):
+def _compile_example(tmp_path, name="benchmark_b200"):
     import subprocess
-    exe = str(tmp_path / "benchmark_b200")
+    exe = str(tmp_path / name)
     subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "benchmark_b200.c"), "-L", PKG_DIR, "-lsahbvh_b200",
+                           os.path.join(ROOT, "examples", name + ".c"), "-L", PKG_DIR, "-lsahbvh_b200",
                            "-Wl,-rpath," + PKG_DIR, "-lm", "-o", exe])
     return exe
 
@@ -383,6 +383,10 @@ def test_c_example_compiles_and_links(pkg, tmp_path):
     exe = _compile_example(tmp_path)
     if pkg.device_count() == 0:     # no GPU here: the binary must refuse loudly instead of falling back to a CPU path
         out = subprocess.run([exe, "1", "5000", "5000", "5000"], capture_output=True, text=True, cwd=str(tmp_path))
+        assert out.returncode != 0 and "no usable CUDA device" in out.stderr
+    exe = _compile_example(tmp_path, "render_multi_b200")     # main.c's render driver on N GPUs (gpu_bvh_set)
+    if pkg.device_count() == 0:
+        out = subprocess.run([exe], capture_output=True, text=True, cwd=str(tmp_path))
         assert out.returncode != 0 and "no usable CUDA device" in out.stderr
 
 

@@ -12,6 +12,7 @@ import __graft_entry__ as g  # noqa: E402
 import torch
 pkg = g.load_pkg()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+pkg.set_keep_binary_tree(True)
 pkg.srand(1)
 s = pkg.benchmark_scene(n)
 bvh = pkg.GpuBvh.build(s, n, 0, n, 0)
@@ -40,3 +41,19 @@ for mode in (pkg.PRIMARY_PACKET, pkg.PRIMARY_PER_RAY):
     if ref is None:
         ref = h
     print(f"mode {mode}: {np.mean(ms):.4f} ms (min {np.min(ms):.4f})  {W * H / np.mean(ms) / 1e6:.2f} Grays/s  same_as_first {same}", flush=True)
+
+pkg.set_primary_mode(pkg.PRIMARY_PACKET)
+ids = torch.empty((W * H,), dtype=torch.int32, device="cuda")
+for _ in range(3):
+    bvh.trace_primary_dev_prims(cam, W, H, 0, H, 0, ids.data_ptr(), stream)
+torch.cuda.synchronize()
+ms = []
+for _ in range(10):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    bvh.trace_primary_dev_prims(cam, W, H, 0, H, 0, ids.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms.append(e0.elapsed_time(e1))
+print(f"ids only: {np.mean(ms):.4f} ms (min {np.min(ms):.4f})  same ids {bool((ids.cpu().numpy() == ref.view(np.int32).reshape(-1, 8)[:, 1]).all())}", flush=True)
