@@ -376,6 +376,8 @@ class FrameGather:
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.count = torch.zeros(1, dtype=torch.int64, device="cuda")
         self.cons = torch.cuda.Stream()
+        self.cons_done = [None, None]
+        self.own_done = None
         if self.ok:
             self.flags = self.ptrs[2]
             self.consumed = self.flags + 8 * world
@@ -384,6 +386,39 @@ class FrameGather:
                     pkg.peer_signal(self.flags + 8 * r, 0, env.stream)
                 torch.cuda.synchronize()
             dist.barrier()
+
+    # Ordering rules.  A device-side spin wait (sahbvh_peer_wait) may only depend on ANOTHER GPU: two streams of one
+    # device can share a hardware queue, so a spinning kernel ahead of the kernel it waits for would dead-lock until
+    # its timeout.  Rank 0's own band -> consumer and consumer -> rank 0's next frame are therefore ordered by CUDA
+    # events; flags carry only cross-GPU edges (bands of ranks 1.. -> consumer, consumed -> ranks 1..).
+    def wait_reusable(self, k, timeout_ms):
+        """before overwriting buffer k&1: frame k-2 must have been consumed"""
+        if k <= 2:
+            return
+        if self.env.rank == 0:
+            self.env.main_stream.wait_event(self.cons_done[k & 1])
+        else:
+            self.env.pkg.peer_wait(self.consumed, 1, k - 2, timeout_ms, self.status.data_ptr(), self.env.stream)
+
+    def band_done(self, k):
+        """this rank's band of frame k is in place (enqueued behind the kernel that writes it)"""
+        if self.env.rank == 0:
+            self.own_done = self.env.torch.cuda.Event()
+            self.own_done.record(self.env.main_stream)
+        else:
+            self.env.pkg.peer_signal(self.flags + 8 * self.env.rank, k, self.env.stream)
+
+    def consumer_begin(self, k, timeout_ms):
+        """rank 0: the consumer stream advances once every band of frame k has landed"""
+        self.cons.wait_event(self.own_done)
+        if self.env.world > 1:
+            self.env.pkg.peer_wait(self.flags + 8, self.env.world - 1, k, timeout_ms, self.status.data_ptr(), self.cons.cuda_stream)
+
+    def consumer_end(self, k):
+        self.env.pkg.peer_signal(self.consumed, k, self.cons.cuda_stream)
+        ev = self.env.torch.cuda.Event()
+        ev.record(self.cons)
+        self.cons_done[k & 1] = ev
 
     def frames(self, bvh, cam, W, H, k_steps, d_records, flush=True, timeout_ms=10000):
         """K frames of rows sharded over the ranks; returns (event0, event1) around them on the main stream."""
@@ -398,15 +433,13 @@ class FrameGather:
             self.frame_no += 1
             k = self.frame_no
             buf = self.ptrs[k & 1]
-            if k > 2:
-                pkg.peer_wait(self.consumed, 1, k - 2, timeout_ms, self.status.data_ptr(), env.stream)
+            self.wait_reusable(k, timeout_ms)
             bvh.trace_primary_dev_prims(cam, W, H, y0, y1, d_records, buf + y0 * W * 4, env.stream)
-            pkg.peer_signal(self.flags + 8 * env.rank, k, env.stream)
+            self.band_done(k)
             if env.rank == 0:
-                cs = self.cons.cuda_stream
-                pkg.peer_wait(self.flags, env.world, k, timeout_ms, self.status.data_ptr(), cs)
-                pkg.count_prims_dev(buf, W * H, self.count.data_ptr(), cs)
-                pkg.peer_signal(self.consumed, k, cs)
+                self.consumer_begin(k, timeout_ms)
+                pkg.count_prims_dev(buf, W * H, self.count.data_ptr(), self.cons.cuda_stream)
+                self.consumer_end(k)
         if env.rank == 0:
             env.main_stream.wait_stream(self.cons)
         e1.record()
@@ -799,16 +832,17 @@ def config5_multi(env, gather):
         for sidx in range(spp):
             bvh.render_frame_dev(cam, W, H, y0, y1, 5, 1000 + sidx, d_rgba.data_ptr(), stream)
             last = sidx == spp - 1
+            if last and rank != 0 and k > 1:      # the single RGBA8 frame on rank 0 is rewritten only once frame k-1 was read
+                pkg.peer_wait(gather.consumed, 1, k - 1, 60000, gather.status.data_ptr(), stream)
             rc = pkg.lib.gpu_accumulate_dev(C.c_void_p(d_acc.data_ptr()), C.c_int(sidx + 1), C.c_void_p(d_rgba.data_ptr()), C.c_int64(npx),
                                             C.c_void_p((fb + y0 * W * 4) if last else d_avg.data_ptr()), C.c_void_p(stream))
             assert rc == 0
-        pkg.peer_signal(gather.flags + 8 * rank, k, stream)
+        gather.band_done(k)
         if rank == 0:
-            cs = gather.cons.cuda_stream
-            pkg.peer_wait(gather.flags, world, k, 60000, gather.status.data_ptr(), cs)
+            gather.consumer_begin(k, 60000)
             with torch.cuda.stream(gather.cons):
                 h_frame.copy_(fb_tensor, non_blocking=True)
-            pkg.peer_signal(gather.consumed, k, cs)
+            gather.consumer_end(k)
             env.main_stream.wait_stream(gather.cons)
 
     one_frame()

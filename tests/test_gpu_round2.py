@@ -13,6 +13,7 @@
 import ctypes as C
 import json
 import os
+import time
 
 import numpy as np
 import pytest
@@ -312,22 +313,34 @@ def test_c_example_render_driver_on_a_device_set(gpu, tmp_path):
 
 def test_peer_wait_and_signal_on_one_device(gpu):
     """sahbvh_peer_wait: the stream advances once the flags are there; a flag that never arrives ends in the
-    timeout status, not in a hung stream."""
+    timeout status, not in a hung stream.  The blocking case is released by HOST stores into pinned flags: two
+    streams of one device may share a hardware queue, so a spin-wait must never depend on a kernel of another
+    stream of the same device (bench.py orders same-device work with events for that reason)."""
     import torch
-    flags = torch.zeros(4, dtype=torch.int64, device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    side = torch.cuda.Stream()
-    main = torch.cuda.current_stream()
-    gpu.peer_wait(flags.data_ptr(), 4, 3, 4000, status.data_ptr(), main.cuda_stream)     # blocks `main` on the device
-    done = torch.cuda.Event()
-    done.record(main)
-    assert not done.query()
-    with torch.cuda.stream(side):
-        for r in range(4):
-            gpu.peer_signal(flags.data_ptr() + 8 * r, 3, side.cuda_stream)
+    main, side = torch.cuda.Stream(), torch.cuda.Stream()
+    # (1) flags signalled by kernels (sahbvh_peer_signal) before the wait is enqueued: passes at once
+    flags = torch.zeros(4, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for r in range(4):
+        gpu.peer_signal(flags.data_ptr() + 8 * r, 3, side.cuda_stream)
+    side.synchronize()
+    gpu.peer_wait(flags.data_ptr(), 4, 3, 4000, status.data_ptr(), main.cuda_stream)
     torch.cuda.synchronize()
     assert int(status.item()) == 0 and flags.tolist() == [3, 3, 3, 3]
-    gpu.peer_wait(flags.data_ptr(), 4, 4, 50, status.data_ptr(), main.cuda_stream)       # never signalled: 50 ms timeout
+    # (2) the wait blocks the stream until the last flag arrives (host writes into page-locked memory)
+    hflags = torch.zeros(4, dtype=torch.int64).pin_memory()
+    gpu.peer_wait(hflags.data_ptr(), 4, 7, 20000, status.data_ptr(), main.cuda_stream)
+    done = torch.cuda.Event()
+    done.record(main)
+    hflags[:3] = 7
+    time.sleep(0.2)
+    assert not done.query()
+    hflags[3] = 9                                                                       # >= value releases it
+    main.synchronize()
+    assert done.query() and int(status.item()) == 0
+    # (3) never signalled: 50 ms timeout
+    gpu.peer_wait(flags.data_ptr(), 4, 4, 50, status.data_ptr(), main.cuda_stream)
     torch.cuda.synchronize()
     assert int(status.item()) == 1
 
