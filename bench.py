@@ -619,6 +619,17 @@ def run_b200(args):
     compulsory_bytes = 32 * n_local + info["n_wide"] * 128 + (info["n_spheres"] + 1) * 16
     touched_bytes = 128 * stats["inner_visits"] + 16 * stats["sphere_tests"] + 32 * n_local   # 128-byte 4-wide nodes
     rec = traffic_record("k_trace_primary_packet", W, rows, args.spheres) if world == 1 else None
+    scaled_from = None
+    if rec is None and args.spheres == N_SPHERES:
+        # N > 1 (or another frame of the same scene): the weak-scaled frame keeps the pixel pitch, so a band's tiles do the
+        # same work as the headline frame's; the instruction count is the headline capture scaled by the tile count
+        base = traffic_record("k_trace_primary_packet", WIDTH, HEIGHT, N_SPHERES)
+        if base and base.get("warp_inst_per_launch"):
+            base_tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 7) // 8)
+            rec = dict(base)
+            rec["warp_inst_per_launch"] = base["warp_inst_per_launch"] * tiles / base_tiles
+            rec["dram_bytes_per_launch"] = None
+            scaled_from = f"ESTIMATE: the ncu count of the {WIDTH}x{HEIGHT} capture x {tiles}/{base_tiles} tiles (same scene, same pixel pitch)"
     sm_mhz = clk.get("sm_mhz") or sm_max
     slots = 4.0 * peaks["sm_count"] * sm_mhz * 1e6          # warp-instruction issue slots per second: 4 schedulers per SM
     if rec and rec.get("warp_inst_per_launch"):
@@ -635,6 +646,9 @@ def run_b200(args):
                     "in this run)",
             "warp_inst_per_launch": inst, "ncu_issue_active_pct": rec.get("issue_active_pct_ncu"), "inst_source": rec.get("inst_source"),
         }
+        if scaled_from:
+            roofline["inst_scaled"] = scaled_from
+            roofline["traffic_note"] = "no DRAM capture for this frame size"
     else:
         roofline = {
             "kernel": "k_trace_primary_packet", "bound": "hbm",

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     "sahbvh_host_alloc", "sahbvh_host_free", "sahbvh_host_pin", "sahbvh_host_unpin",
     "gpu_trace_closest_hit_prims", "gpu_trace_closest_hit_dev_prims", "gpu_trace_primary_prims", "gpu_trace_primary_tprim",
-    "gpu_hits_from_prims", "sahbvh_set_keep_binary_tree", "sahbvh_peer_wait", "gpu_count_prims_dev",
+    "gpu_hits_from_prims", "sahbvh_set_keep_binary_tree", "sahbvh_set_l2_persist_bytes", "sahbvh_peer_wait", "gpu_count_prims_dev",
     "gpu_bvh_replicate", "gpu_bvh_build_replicated", "gpu_bvh_set_free", "gpu_bvh_set_size", "gpu_bvh_set_get",
     "sahbvh_shard_range", "sahbvh_shard_rows", "gpu_trace_primary_multi", "gpu_trace_primary_prims_multi",
     "gpu_trace_primary_prims_multi_dev", "gpu_trace_closest_hit_multi", "gpu_trace_closest_hit_prims_multi",
@@ -176,6 +176,11 @@ def set_keep_binary_tree(keep: bool):
 
 
 TPRIM_DT = np.dtype([("t", np.float32), ("prim", np.int32)])    # gpu_tprim
+
+
+def set_l2_persist_bytes(nbytes: int):
+    """persisting-L2 window over the top `nbytes` of the wide tree for every trace launch (0 = off)"""
+    _check(lib.sahbvh_set_l2_persist_bytes(C.c_uint64(nbytes)), "sahbvh_set_l2_persist_bytes")
 
 
 def set_primary_mode(mode: int):

@@ -32,6 +32,7 @@ struct gpu_bvh {
     /* path-loop work buffers (render.cu), one allocation grown on demand */
     void *d_render;
     size_t render_cap;
+    size_t l2_limit_applied; /* persisting-L2 set-aside this handle asked the device for (sahbvh_set_l2_persist_bytes) */
 };
 
 struct DeviceGuard {

@@ -260,6 +260,9 @@ k_trace_rays_coop(const float *__restrict__ nodes, const float *__restrict__ sph
 #ifndef WIDE_REFILL_MIN
 #define WIDE_REFILL_MIN 4
 #endif
+#ifndef WIDE_TOP_NODES
+#define WIDE_TOP_NODES 0 /* > 0: that many top nodes in shared memory (experiment, see the kernel) */
+#endif
 
 __device__ __forceinline__ void ld_wide_node(const uint32_t *__restrict__ nodes, int32_t node, uint32_t (&w)[16])
 {
@@ -277,13 +280,22 @@ __device__ __forceinline__ void ld_wide_node(const uint32_t *__restrict__ nodes,
 
 template <bool COUNT>
 __global__ void __launch_bounds__(WIDE_WARPS * 32, WIDE_MIN_BLOCKS)
-k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ spheres4, const float *__restrict__ special,
+k_trace_rays_wide(const uint32_t *__restrict__ nodes, int n_wide, const float *__restrict__ spheres4, const float *__restrict__ special,
                   int n_special, SahScene sc, const float *__restrict__ rays, long long n, gpu_hit *__restrict__ out,
                   int32_t *__restrict__ prims_out, unsigned long long *next_ray, unsigned long long *counters)
 {
     /* out != NULL: 32-byte records; else prims_out receives the 4-byte primitive id per ray (point and normal are
      * never computed: sahbvh_hit_from_prim / gpu_hits_from_prims derive them on demand) */
     __shared__ int32_t s_stack[WIDE_FAST_STACK][WIDE_WARPS * 32];
+#if WIDE_TOP_NODES > 0
+    /* experiment (north_star "top BVH levels in shared memory"): the first WIDE_TOP_NODES nodes of the breadth-first
+     * numbering (3 wide levels = 85 nodes = 5.3 KB) are read from shared memory instead of L1/L2; measured in
+     * DESIGN.md section 4, off by default */
+    __shared__ uint4 s_top[WIDE_TOP_NODES * 4];
+    const int top_n = n_wide < WIDE_TOP_NODES ? n_wide : WIDE_TOP_NODES;
+    for (int i = threadIdx.x; i < top_n * 4; i += WIDE_WARPS * 32) s_top[i] = __ldg(reinterpret_cast<const uint4 *>(nodes) + i);
+    __syncthreads();
+#endif
     int32_t slow[SAH_WIDE_STACK_MAX - WIDE_FAST_STACK];
     const SahStack stk = {&s_stack[0][threadIdx.x], WIDE_WARPS * 32, WIDE_FAST_STACK, slow};
     const unsigned full = 0xffffffffu;
@@ -372,6 +384,14 @@ k_trace_rays_wide(const uint32_t *__restrict__ nodes, const float *__restrict__ 
         }
         if (node >= 0) {
             uint32_t w[16];
+#if WIDE_TOP_NODES > 0
+            if (node < top_n) {
+                const uint4 *q = s_top + node * 4;
+                const uint4 a = q[0], b4 = q[1], c4 = q[2], d4 = q[3];
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b4.x; w[5] = b4.y; w[6] = b4.z; w[7] = b4.w;
+                w[8] = c4.x; w[9] = c4.y; w[10] = c4.z; w[11] = c4.w; w[12] = d4.x; w[13] = d4.y; w[14] = d4.z; w[15] = d4.w;
+            } else
+#endif
             ld_wide_node(nodes, node, w);
             node = sah_wide_visit<COUNT>(r, w, node, stk, sp, best_s, pend0, pend1, stall_at, &cnt);
             if (stall_at >= 0) node = -2 - node;
@@ -423,7 +443,14 @@ k_trace_primary(const float *__restrict__ nodes, const float *__restrict__ spher
  * (and, for a would-be winner, the reference-exact leaf box test) on each candidate, so the
  * result is the same "best over leaves whose own tests pass" as the per-ray kernel.
  */
+#ifndef PKT_WARPS
 #define PKT_WARPS 4        /* the block's 4 warps own a 2x2 group of tiles = 32 x 16 pixels (their frusta overlap more than a 4x1 strip's) */
+#endif
+#define PKT_GROUP_ROWS (PKT_WARPS / 2)   /* a block = 2 tiles across (one 32-pixel = 128-byte id row) x PKT_GROUP_ROWS tiles down */
+static_assert(PKT_WARPS == 2 || PKT_WARPS == 4 || PKT_WARPS == 8, "PKT_WARPS");
+#ifndef PKT_WARP_OUT
+#define PKT_WARP_OUT 0     /* 1: every warp stores its own tile (64-byte id segments, no block barrier); tuning experiment */
+#endif
 #ifndef PKT_STACK
 #define PKT_STACK 512
 #endif
@@ -460,15 +487,27 @@ static int sahbvh_packet_dfs_from(int tree_depth)
 }
 static_assert(PKT_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_STACK too small for the deepest admissible tree");
 
+/* warp-wide min / max of non-NaN floats with ONE redux.sync each: the bit pattern of a float, with the magnitude bits
+ * flipped when the sign is set, orders as a signed integer exactly like the float (-0 < +0, infinities included) */
+__device__ __forceinline__ int float_order_key(float v)
+{
+    const int i = __float_as_int(v);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
 __device__ __forceinline__ float warp_min(float v)
 {
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const int k = __reduce_min_sync(0xffffffffu, float_order_key(v));
+    return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
 }
 __device__ __forceinline__ float warp_max(float v)
 {
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const int k = __reduce_max_sync(0xffffffffu, float_order_key(v));
+    return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
+}
+/* same for values known to be >= +0 (or +inf): the raw bits already order as unsigned integers */
+__device__ __forceinline__ float warp_max_nonneg(float v)
+{
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
 }
 
 /* 32-byte record with ONE 256-bit store (sm_100 st.global.v8): a warp writing a 32-pixel row emits 1 KiB contiguous */
@@ -504,7 +543,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
     unsigned long long hits = 0;
     const unsigned groups_x = (unsigned)(tiles_x + 1) >> 1;
     const int gy = (int)(blockIdx.x / groups_x), gx = (int)(blockIdx.x % groups_x);
-    const int ty = gy * 2 + (warp >> 1), tx = gx * 2 + (warp & 1);
+    const int ty = gy * PKT_GROUP_ROWS + (warp >> 1), tx = gx * 2 + (warp & 1);
     if (tx < tiles_x && ty < tiles_y) {
         int32_t *stack = s_stack[warp];
         /* ---- this lane's 4 rays: pixel (tx*16 + (k&1)*8 + lane%8, y0 + ty*8 + (k>>1)*4 + lane/8) ---- */
@@ -648,24 +687,37 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                 for (int k = 0; k < PKT_K; k++)
                     if (valid & (1u << k))
                         w = fmaxf(w, s_bp[warp][k][lane] >= 0 ? F_FMA(s_bt[warp][k][lane], SAH_REL_CULL, cull_abs) : INFINITY);
-                pkt_best_s = warp_max(w);
+                pkt_best_s = warp_max_nonneg(w);   /* w >= 0: t > 1e-6, cull_abs >= 0 */
             }
         }
     }
-    /* ---- results: the block's 32 x 16 pixels leave through shared memory, one 32-pixel ROW per warp instruction
-     * (128 contiguous bytes of ids, 1 KiB of records), whichever warp traced them -- the ids may be going to another
-     * GPU's frame over NVLink or to pinned host memory over PCIe, where 32-byte segments waste the link. ---- */
+    /* ---- results: the block's 32 x (8 PKT_GROUP_ROWS) pixels leave through shared memory, one 32-pixel ROW per warp
+     * instruction (128 contiguous bytes of ids, 1 KiB of records), whichever warp traced them -- the ids may be going to
+     * another GPU's frame over NVLink or to pinned host memory over PCIe, where 32-byte segments waste the link. ---- */
+#if PKT_WARP_OUT
+    __syncwarp();
+    const int out_rows = PKT_TILE_H / 2;               /* a warp instruction covers two 16-pixel rows of the warp's own tile */
+#else
     __syncthreads();
-    const int bx = gx * 32 + lane;
+    const int out_rows = PKT_TILE_H * PKT_GROUP_ROWS / PKT_WARPS;
+#endif
 #pragma unroll 1
-    for (int q = 0; q < 4; q++) {
-        const int r = warp * 4 + q;                    /* row of the block */
-        const int py = y0 + gy * 16 + r;
+    for (int q = 0; q < out_rows; q++) {
+#if PKT_WARP_OUT
+        const int r = (warp >> 1) * PKT_TILE_H + q * 2 + (lane >> 4); /* row of the block */
+        const int bx = gx * 32 + (warp & 1) * 16 + (lane & 15);
+        const int lx = (warp & 1) * 16 + (lane & 15);                /* column of the block */
+#else
+        const int r = warp * out_rows + q;
+        const int bx = gx * 32 + lane;
+        const int lx = lane;
+#endif
+        const int py = y0 + gy * (PKT_TILE_H * PKT_GROUP_ROWS) + r;
         if (py >= y1 || bx >= width) continue;
-        /* pixel (lane, r) of the block was ray k of lane l2 of warp w2 (tile layout above) */
-        const int w2 = (r >> 3) * 2 + (lane >> 4);
-        const int k = (((r & 7) >> 2) << 1) | ((lane >> 3) & 1);
-        const int l2 = ((r & 3) << 3) | (lane & 7);
+        /* pixel (lx, r) of the block was ray k of lane l2 of warp w2 (tile layout above) */
+        const int w2 = (r >> 3) * 2 + (lx >> 4);
+        const int k = (((r & 7) >> 2) << 1) | ((lx >> 3) & 1);
+        const int l2 = ((r & 3) << 3) | (lx & 7);
         const int32_t bp = s_bp[w2][k][l2];
         const float bt = s_bt[w2][k][l2];
         const size_t pix = (size_t)(py - y0) * (size_t)width + (size_t)bx;
@@ -1104,6 +1156,61 @@ SahScene sahbvh_make_scene(const gpu_bvh_info &info)
     return sc;
 }
 
+/* north_star (2) "top BVH levels in ... L2-persisting windows": the wide trees are numbered breadth first, so their
+ * top levels are a PREFIX of the node array.  With sahbvh_set_l2_persist_bytes(B > 0) the trace launches run with an
+ * access-policy window over the first B bytes of the tree they read (hit ratio 1, persisting; everything else
+ * streaming) and the device sets aside as much L2.  Off by default: measured in DESIGN.md section 4 (it only matters
+ * when the tree is larger than the 126 MB L2, i.e. at 10 M spheres). */
+static std::atomic<size_t> g_l2_persist{0};
+extern "C" int sahbvh_set_l2_persist_bytes(uint64_t bytes)
+{
+    g_l2_persist.store((size_t)bytes);
+    return SAHBVH_OK;
+}
+struct L2Window {
+    cudaStream_t st;
+    bool on;
+    L2Window(gpu_bvh *b, cudaStream_t s, const void *base, size_t tree_bytes) : st(s), on(false)
+    {
+        size_t want = g_l2_persist.load();
+        if (want == 0 || !base) {
+            if (b->l2_limit_applied) { /* switched off again: give the set-aside back */
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+                cudaCtxResetPersistingL2Cache();
+                b->l2_limit_applied = 0;
+            }
+            return;
+        }
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, b->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, b->device);
+        if (want > tree_bytes) want = tree_bytes;
+        if (want > (size_t)max_persist) want = (size_t)max_persist;
+        if (want > (size_t)max_window) want = (size_t)max_window;
+        if (want == 0) return;
+        if (b->l2_limit_applied != want) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { (void)cudaGetLastError(); return; }
+            b->l2_limit_applied = want;
+        }
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof v);
+        v.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+        v.accessPolicyWindow.num_bytes = want;
+        v.accessPolicyWindow.hitRatio = 1.0f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        on = true;
+    }
+    ~L2Window()
+    {
+        if (!on) return;
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof v);
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v); /* num_bytes 0: later launches of the stream are unaffected */
+    }
+};
+
 static int trace_grid(const gpu_bvh *b, long long n)
 {
     long long blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;
@@ -1134,11 +1241,12 @@ int sahbvh_launch_rays(gpu_bvh *b, const void *d_rays, long long n, void *d_out,
         if (blocks > cap) blocks = cap;
         unsigned long long *ctr = b->d_counters + 8 + (b->next_counter++ & 63);
         CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
+        L2Window win(b, st, b->d_wide, (size_t)b->n_wide * 64);
         if (count)
-            k_trace_rays_wide<true><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->d_spheres4, b->d_special, b->n_special, sc,
+            k_trace_rays_wide<true><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->n_wide, b->d_spheres4, b->d_special, b->n_special, sc,
                                                                                  (const float *)d_rays, n, (gpu_hit *)d_out, nullptr, ctr, b->d_counters);
         else
-            k_trace_rays_wide<false><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->d_spheres4, b->d_special, b->n_special, sc,
+            k_trace_rays_wide<false><<<(unsigned)blocks, WIDE_WARPS * 32, 0, st>>>(b->d_wide, b->n_wide, b->d_spheres4, b->d_special, b->n_special, sc,
                                                                                   (const float *)d_rays, n, (gpu_hit *)d_out,
                                                                                   d_out ? nullptr : (int32_t *)d_prims, ctr, nullptr);
     } else if (g_ray_mode.load() == SAHBVH_RAYS_COOP) {
@@ -1213,13 +1321,14 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
     const SahScene sc = sahbvh_make_scene(b->info);
     if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
         /* one CTA per 32 x 16 pixel group (2 x 2 tiles of 16 x 8) */
-        const long long groups = (long long)((width + 31) / 32) * ((y1 - y0 + 2 * PKT_TILE_H - 1) / (2 * PKT_TILE_H));
+        const long long groups = (long long)((width + 31) / 32) * ((y1 - y0 + PKT_GROUP_ROWS * PKT_TILE_H - 1) / (PKT_GROUP_ROWS * PKT_TILE_H));
         if (groups >= (1ll << 31) - 1) {
             sahbvh_set_error("frame too large for one launch (%lld tile groups): trace it in row bands", groups);
             return SAHBVH_E_ARG;
         }
         const unsigned grid = (unsigned)groups;
         const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth);
+        L2Window win(b, st, b->d_wide_full, (size_t)b->n_wide * 128);
         if (count)
             k_trace_primary_packet<true, true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                out, ids, ids_mode, dfs_from, b->d_counters);

@@ -172,7 +172,10 @@ int sahbvh_peer_read_flags(const void *d_flags, int n, uint64_t *out, void *stre
 /* Device-side wait (no host round trip): `stream` does not advance until all n 64-bit flags at d_flags are >= value.
  * With sahbvh_peer_signal this is the frame loop's back-pressure -- the owner consumes frame k once every band's
  * flag says k, a producer reuses a frame buffer once the owner's "consumed" flag allows it.  Gives up after
- * timeout_ms (0 = 2000) and stores 1 into the 32-bit word *d_status (may be NULL) instead of hanging the stream. */
+ * timeout_ms (0 = 2000) and stores 1 into the 32-bit word *d_status (may be NULL) instead of hanging the stream.
+ * The flags waited for must be written by ANOTHER GPU or by the host: two streams of one device may share a hardware
+ * queue, so a wait ahead of the same device's signalling kernel is not guaranteed to make progress -- order work of
+ * one device with cudaEvents (bench.py's FrameGather and gpu_trace_primary_prims_multi_dev do). */
 int sahbvh_peer_wait(const void *d_flags, int n, uint64_t value, uint32_t timeout_ms, void *d_status, void *stream);
 /* benchmark.c:242-244 over an id buffer that is already on the device: *d_count (uint64) += #(ids >= 0).  Asynchronous. */
 int gpu_count_prims_dev(const void *d_prims, int64_t n, void *d_count, void *stream);
@@ -206,6 +209,12 @@ int sahbvh_set_ray_mode(int mode);
  * Handles created while keep == 0 (the default) do not hold it (64 MB per million spheres); those modes then
  * return SAHBVH_E_ARG on such a handle.  Set keep = 1 BEFORE gpu_bvh_upload / gpu_bvh_build to use them. */
 int sahbvh_set_keep_binary_tree(int keep);
+/* Top-of-tree residency (process-wide, default 0 = off).  The wide trees are numbered breadth first, so their top
+ * levels are a prefix of the node array: with bytes > 0 every trace launch runs with a persisting-L2 access-policy
+ * window over the first `bytes` of the tree it reads (clamped to the tree, to cudaDevAttrMaxPersistingL2CacheSize and
+ * to cudaDevAttrMaxAccessPolicyWindowSize) and the rest of its traffic marked streaming.  Only worth it when the tree
+ * is larger than the L2 (10 M spheres: 320 MB of quantised nodes); results never change. */
+int sahbvh_set_l2_persist_bytes(uint64_t bytes);
 /* Ray generation only (parity aid for ray.c): writes Ray records for rows [y0,y1). */
 int gpu_generate_primary_rays(const Camera *cam, int width, int height, int y0, int y1, Ray *out, int device);
 

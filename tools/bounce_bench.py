@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--kind", default="bounce", choices=["bounce", "bench", "primary"])
     ap.add_argument("--stride", type=int, default=1, help="generate rays*stride rays and keep every stride-th")
     ap.add_argument("--sort", default="", choices=["", "morton", "morton_dir", "shuffle"], help="reorder the rays on the host before tracing")
+    ap.add_argument("--l2-mb", default="", help="comma list of persisting-L2 window sizes (MiB) to time after the default run (sahbvh_set_l2_persist_bytes)")
     ap.add_argument("--tile", default="", help="WxH: take the primary hits in pixel-tile order (e.g. 8x4) instead of row-major")
     args = ap.parse_args()
     import torch
@@ -100,6 +101,19 @@ def main():
             same = bool((ref.view(np.uint32) == h.view(np.uint32)).all())
         print(f"mode {mode}: {ms:8.3f} ms  {n / ms / 1e6:7.3f} Grays/s  nodes/ray {st['inner_visits'] / n:6.1f} "
               f"spheres/ray {st['sphere_tests'] / n:5.2f} max_stack {st['max_stack']} max_visits {st['max_visits']} same_as_first {same}", flush=True)
+        for mb in [int(v) for v in args.l2_mb.split(",") if v]:
+            pkg.set_l2_persist_bytes(mb << 20)
+            for _ in range(2):
+                bvh.trace_closest_hit_dev(d_rays.data_ptr(), n, d_hits.data_ptr(), stream)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                bvh.trace_closest_hit_dev(d_rays.data_ptr(), n, d_hits.data_ptr(), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            same_l2 = bool((d_hits.cpu().numpy().view(np.uint32) == ref.view(np.uint32)).all())
+            print(f"mode {mode} with a {mb} MiB persisting-L2 window over the top of the tree: {e0.elapsed_time(e1) / args.steps:8.3f} ms  same {same_l2}", flush=True)
+        pkg.set_l2_persist_bytes(0)
 
 
 if __name__ == "__main__":

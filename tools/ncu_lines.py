@@ -14,7 +14,7 @@ fname, hdr, lines = None, None, []
 for r in rows:
     if not r:
         continue
-    if r[0] == "File Name":
+    if r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
     elif r[0] == "Line No":
         hdr = r
