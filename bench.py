@@ -378,6 +378,8 @@ class FrameGather:
         self.cons = torch.cuda.Stream()
         self.cons_done = [None, None]
         self.own_done = None
+        self.root_share = 1.0      # calibrate() shortens rank 0's band by the consumer's cost
+        self.calibration = None
         if self.ok:
             self.flags = self.ptrs[2]
             self.consumed = self.flags + 8 * world
@@ -420,11 +422,40 @@ class FrameGather:
         ev.record(self.cons)
         self.cons_done[k & 1] = ev
 
+    def calibrate(self, bvh, cam, W, H, d_records, reps=5):
+        """Load balance: rank 0 traces its band AND consumes every frame, so its band is shortened until all ranks
+        finish a frame together.  t = event time of an equal band (mean over ranks), c = event time of the consumer's
+        pass over the whole frame on rank 0; root_share = 1 - (c/t)(N-1)/N (sahbvh_shard_rows_weighted)."""
+        env, pkg, torch = self.env, self.env.pkg, self.env.torch
+        y0, y1 = pkg.shard_rows(H, env.rank, env.world)
+        buf = self.ptrs[0]
+        fn = lambda: bvh.trace_primary_dev_prims(cam, W, H, y0, y1, d_records, buf + y0 * W * 4, env.stream)
+        env.fence()
+        t = time_steps(torch, fn, reps, 2, env.flush)[0] / reps
+        env.fence()
+        c = 0.0
+        if env.rank == 0:
+            c = time_steps(torch, lambda: pkg.count_prims_dev(buf, W * H, self.count.data_ptr(), env.stream), reps, 2, env.flush)[0] / reps
+        tc = torch.tensor([t / env.world, c], dtype=torch.float64, device="cuda")
+        env.dist.all_reduce(tc, op=env.dist.ReduceOp.SUM)
+        t_mean, c = float(tc[0].item()), float(tc[1].item())
+        share = 1.0 - (c / t_mean) * (env.world - 1) / env.world if t_mean > 0 else 1.0
+        self.root_share = min(1.0, max(0.5, share))
+        self.calibration = {"equal_band_ms": t_mean, "consumer_ms": c, "root_share": self.root_share,
+                            "rows": [pkg.shard_rows_weighted(H, r, env.world, self.root_share) for r in range(env.world)]}
+        self.count.zero_()
+        env.fence()
+        return self.calibration
+
+    def band(self, H, rank=None):
+        rank = self.env.rank if rank is None else rank
+        return self.env.pkg.shard_rows_weighted(H, rank, self.env.world, self.root_share)
+
     def frames(self, bvh, cam, W, H, k_steps, d_records, flush=True, timeout_ms=10000):
         """K frames of rows sharded over the ranks; returns (event0, event1) around them on the main stream."""
         env, pkg, torch = self.env, self.env.pkg, self.env.torch
         assert W * H <= self.max_pixels
-        y0, y1 = pkg.shard_rows(H, env.rank, env.world)
+        y0, y1 = self.band(H)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(k_steps):
@@ -502,7 +533,8 @@ def run_b200(args):
     assert rows * world == H
     n_local = rows * W
     total_rays = W * H
-    hits_local = torch.empty((max(n_local, WIDTH * HEIGHT // world + 16 * WIDTH), 8), dtype=torch.float32, device="cuda")
+    # room for the largest band of the load-balanced frame loop (the ranks other than the root take a little more than 1/N)
+    hits_local = torch.empty((max(n_local + n_local // 4 + 16 * W, WIDTH * HEIGHT // world + 16 * WIDTH), 8), dtype=torch.float32, device="cuda")
 
     gather = None
     if dist_on:
@@ -521,6 +553,8 @@ def run_b200(args):
         e1.record()
         return e0, e1
 
+    if gather is not None:
+        gather.calibrate(bvh, cam, W, H, hits_local.data_ptr())
     run_steps(args.warmup)
     env.fence()
     if gather is not None:
@@ -532,9 +566,16 @@ def run_b200(args):
     env.fence()
     launches = pkg.kernel_launches() - launches0
     clk = clocks.stop()
-    ms_per_step = env.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    my_ms = e0.elapsed_time(e1) / args.steps
+    ms_per_step = env.max_over_ranks(my_ms)
     value = total_rays / (ms_per_step * 1e-3) / 1e9
-    local_hits = int((hits_local[:n_local, 1].view(torch.int32) >= 0).sum().item())
+    per_rank_ms = [my_ms]
+    if dist_on:
+        t_all = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(t_all, torch.tensor([my_ms], dtype=torch.float64, device="cuda"))
+        per_rank_ms = [float(t.item()) for t in t_all]
+    fy0, fy1 = gather.band(H) if gather is not None else (y0, y1)       # the band this rank traced in the timed loop
+    local_hits = int((hits_local[:(fy1 - fy0) * W, 1].view(torch.int32) >= 0).sum().item())
     frame_hits = env.sum_over_ranks(local_hits)
     consumer = None
     if dist_on:
@@ -544,7 +585,7 @@ def run_b200(args):
                             "reusing a frame buffer (double buffering with back-pressure)",
                     "hits_counted": consumed_total, "hits_expected": frame_hits * args.steps,
                     "ok": (consumed_total == frame_hits * args.steps) if rank == 0 else None,
-                    "wait_timeouts": gather.timeouts()}
+                    "wait_timeouts": gather.timeouts(), "load_balance": gather.calibration, "ms_per_step_by_rank": per_rank_ms}
 
     # ---- the dominant kernel alone (per-launch events, L2 flushed between launches): records and ids-only
     kn = max(3, min(args.steps, 10))

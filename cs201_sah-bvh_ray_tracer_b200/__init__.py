@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "gpu_trace_closest_hit_prims", "gpu_trace_closest_hit_dev_prims", "gpu_trace_primary_prims", "gpu_trace_primary_tprim",
     "gpu_hits_from_prims", "sahbvh_set_keep_binary_tree", "sahbvh_set_l2_persist_bytes", "sahbvh_peer_wait", "gpu_count_prims_dev",
     "gpu_bvh_replicate", "gpu_bvh_build_replicated", "gpu_bvh_set_free", "gpu_bvh_set_size", "gpu_bvh_set_get",
-    "sahbvh_shard_range", "sahbvh_shard_rows", "gpu_trace_primary_multi", "gpu_trace_primary_prims_multi",
+    "sahbvh_shard_range", "sahbvh_shard_rows", "sahbvh_shard_rows_weighted", "gpu_trace_primary_multi", "gpu_trace_primary_prims_multi",
     "gpu_trace_primary_prims_multi_dev", "gpu_trace_closest_hit_multi", "gpu_trace_closest_hit_prims_multi",
     "gpu_benchmark_with_bvh_multi", "gpu_render_frame_multi",
     # include/sahbvh_ref_api.h
@@ -96,6 +96,7 @@ def _load():
     lib.gpu_bvh_set_free.restype = None
     lib.gpu_bvh_set_get.restype = C.c_void_p
     lib.sahbvh_shard_rows.restype = None
+    lib.sahbvh_shard_rows_weighted.restype = None
     lib.sahbvh_shard_range.restype = None
     return lib
 
@@ -536,6 +537,13 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     lo, hi = C.c_int64(), C.c_int64()
     lib.sahbvh_shard_range(C.c_int64(n), C.c_int(rank), C.c_int(world), C.byref(lo), C.byref(hi))
     return int(lo.value), int(hi.value)
+
+
+def shard_rows_weighted(height: int, rank: int, world: int, root_share: float) -> tuple[int, int]:
+    """row band of `rank` when rank 0 takes root_share of an equal share (it also consumes the frame)"""
+    y0, y1 = C.c_int(), C.c_int()
+    lib.sahbvh_shard_rows_weighted(C.c_int(height), C.c_int(rank), C.c_int(world), C.c_double(root_share), C.byref(y0), C.byref(y1))
+    return y0.value, y1.value
 
 
 def shard_rows(height: int, rank: int, world: int) -> tuple[int, int]:

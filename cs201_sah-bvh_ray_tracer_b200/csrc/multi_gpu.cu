@@ -45,6 +45,34 @@ extern "C" void sahbvh_shard_rows(int height, int part, int n_parts, int *y0, in
     *y1 = (int)(b1 * align < height ? b1 * align : height);
 }
 
+/* Uneven bands for a frame loop whose ROOT (part 0) also consumes the assembled frame: the root's band is
+ * root_share (0 < root_share <= 1) of an equal share, the other parts split the rest evenly; same 16-row alignment.
+ * With t = time of an equal band and c = what consuming one frame costs the root, root_share = 1 - (c/t)(N-1)/N
+ * makes every device finish a frame at the same time (bench.py calibrates it in its warm-up). */
+extern "C" void sahbvh_shard_rows_weighted(int height, int part, int n_parts, double root_share, int *y0, int *y1)
+{
+    const int align = 16;
+    if (n_parts < 2 || !(root_share > 0.0) || root_share >= 1.0) {
+        sahbvh_shard_rows(height, part, n_parts, y0, y1);
+        return;
+    }
+    const long long blocks = (height + align - 1) / align;
+    long long b_root = (long long)((double)blocks / n_parts * root_share + 0.5);
+    if (b_root < 1) b_root = blocks >= n_parts ? 1 : 0;
+    if (b_root > blocks) b_root = blocks;
+    const long long rest = blocks - b_root;
+    long long b0, b1;
+    if (part == 0) {
+        b0 = 0;
+        b1 = b_root;
+    } else {
+        b0 = b_root + rest * (part - 1) / (n_parts - 1);
+        b1 = b_root + rest * part / (n_parts - 1);
+    }
+    *y0 = (int)(b0 * align < height ? b0 * align : height);
+    *y1 = (int)(b1 * align < height ? b1 * align : height);
+}
+
 /* ---- worker: one thread pinned to one device of the set ---- */
 struct SetWorker {
     std::thread th;

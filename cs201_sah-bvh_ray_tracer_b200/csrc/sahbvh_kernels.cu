@@ -863,12 +863,31 @@ __global__ void __launch_bounds__(256) k_count_prims(const gpu_hit *__restrict__
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
+/* HBM-streaming reduction (the frame consumer of the multi-GPU loop runs it on 4 bytes per pixel): 128-bit loads,
+ * four in flight per thread; the unaligned head and the tail go through the scalar path */
 __global__ void __launch_bounds__(256) k_count_prim_ids(const int32_t *__restrict__ prims, long long n, unsigned long long *count)
 {
-    unsigned long long c = 0;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) c += prims[i] >= 0;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+    unsigned c = 0;
+    const long long tid = (long long)blockIdx.x * 256 + threadIdx.x, nthr = (long long)gridDim.x * 256;
+    long long head = (long long)((16 - ((uintptr_t)prims & 15)) & 15) / 4;
+    if (head > n) head = n;
+    const int4 *v = reinterpret_cast<const int4 *>(prims + head);
+    const long long nv = (n - head) / 4;
+    long long i = tid;
+    for (; i + 3 * nthr < nv; i += 4 * nthr) {
+        const int4 a = __ldcs(v + i), b = __ldcs(v + i + nthr), d = __ldcs(v + i + 2 * nthr), e = __ldcs(v + i + 3 * nthr);
+        c += (a.x >= 0) + (a.y >= 0) + (a.z >= 0) + (a.w >= 0) + (b.x >= 0) + (b.y >= 0) + (b.z >= 0) + (b.w >= 0);
+        c += (d.x >= 0) + (d.y >= 0) + (d.z >= 0) + (d.w >= 0) + (e.x >= 0) + (e.y >= 0) + (e.z >= 0) + (e.w >= 0);
+    }
+    for (; i < nv; i += nthr) {
+        const int4 a = __ldcs(v + i);
+        c += (a.x >= 0) + (a.y >= 0) + (a.z >= 0) + (a.w >= 0);
+    }
+    if (tid < head) c += prims[tid] >= 0;
+    const long long tail0 = head + nv * 4;
+    if (tail0 + tid < n) c += prims[tail0 + tid] >= 0;   /* < 4 elements */
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1946,8 +1965,9 @@ extern "C" int gpu_count_prims_dev(const void *d_prims, int64_t n, void *d_count
         return SAHBVH_E_ARG;
     }
     if (n == 0) return SAHBVH_OK;
-    long long blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    long long blocks = (n / 16 + 255) / 256;   /* 16 ids per thread and pass */
+    if (blocks > 148 * 4) blocks = 148 * 4;     /* a light grid: the consumer shares the root GPU with the next frame's trace kernel */
+    if (blocks < 1) blocks = 1;
     k_count_prim_ids<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const int32_t *)d_prims, n, (unsigned long long *)d_count);
     g_launches++;
     CU_TRY(cudaGetLastError());

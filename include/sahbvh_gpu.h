@@ -269,6 +269,9 @@ gpu_bvh *gpu_bvh_set_get(gpu_bvh_set *set, int i);   /* borrowed: the set keeps 
 /* the sharding rules: contiguous ray ranges; row bands of whole 16-row blocks (last band takes the remainder) */
 void sahbvh_shard_range(int64_t n, int part, int n_parts, int64_t *lo, int64_t *hi);
 void sahbvh_shard_rows(int height, int part, int n_parts, int *y0, int *y1);
+/* uneven bands when part 0 (the root) also consumes the assembled frame: its band is root_share (0..1] of an equal
+ * share, the others split the rest; root_share = 1 - (c/t)(N-1)/N for consumer cost c and equal-band time t */
+void sahbvh_shard_rows_weighted(int height, int part, int n_parts, double root_share, int *y0, int *y1);
 /* main.c:356-366 over N devices: the whole width x height frame into a HOST buffer (32-byte records / 4-byte ids). */
 int gpu_trace_primary_multi(gpu_bvh_set *set, const Camera *cam, int width, int height, gpu_hit *out);
 int gpu_trace_primary_prims_multi(gpu_bvh_set *set, const Camera *cam, int width, int height, int32_t *prims);

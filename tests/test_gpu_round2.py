@@ -345,6 +345,22 @@ def test_peer_wait_and_signal_on_one_device(gpu):
     assert int(status.item()) == 1
 
 
+def test_count_prims_dev_alignment_and_tails(gpu):
+    """gpu_count_prims_dev (the frame consumer's reduction) reads 128-bit words: unaligned starts, short arrays and
+    tails must count exactly like benchmark.c:242-244's loop."""
+    import torch
+    rng = np.random.default_rng(5)
+    host = rng.integers(-1, 5, size=100003).astype(np.int32)
+    base = torch.from_numpy(host).cuda()
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for off in (0, 1, 2, 3, 5):
+        for n in (0, 1, 3, 4, 15, 16, 17, 1000, 65536, 100003 - off):
+            cnt.zero_()
+            gpu.count_prims_dev(base.data_ptr() + 4 * off, n, cnt.data_ptr(), 0)
+            torch.cuda.synchronize()
+            assert int(cnt.item()) == int((host[off:off + n] >= 0).sum()), (off, n)
+
+
 # ---------------------------------------------------------------- the frame the bench times
 def test_1m_4k_full_frame_kernels_agree_and_oracle_sample(gpu, oracle):
     """The headline workload itself: 1 M spheres, 3840 x 2160.  packet == per-ray == ray-buffer kernel over the

@@ -92,6 +92,21 @@ def test_shard_arithmetic():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+    # weighted bands (the root also consumes the frame): they tile the frame on 16-row boundaries, the root's band is
+    # root_share of an equal share, the others differ by at most one block; share 1 (or world 1) is the equal split
+    for H in (600, 2160, 4320, 6144, 50):
+        for world in (1, 2, 4, 8):
+            for share in (1.0, 0.9, 0.8, 0.5):
+                b = [pkg.shard_rows_weighted(H, k, world, share) for k in range(world)]
+                assert b[0][0] == 0 and b[-1][1] == H
+                assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+                assert all(y0 % 16 == 0 for y0, _ in b)
+                if share == 1.0 or world == 1:
+                    assert b == [pkg.shard_rows(H, k, world) for k in range(world)]
+                elif H >= 16 * world * 4:
+                    rows = [y1 - y0 for y0, y1 in b]
+                    assert abs(rows[0] - H / world * share) <= 16
+                    assert max(rows[1:]) - min(rows[1:]) <= 16 and min(rows[1:]) >= rows[0]
     for H in (600, 2160, 4320, 50, 7):
         for world in (1, 2, 4, 8):
             b = [pkg.shard_rows(H, k, world) for k in range(world)]
