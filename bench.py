@@ -447,15 +447,16 @@ class FrameGather:
         env.fence()
         return self.calibration
 
-    def band(self, H, rank=None):
+    def band(self, H, balanced, rank=None):
         rank = self.env.rank if rank is None else rank
-        return self.env.pkg.shard_rows_weighted(H, rank, self.env.world, self.root_share)
+        return self.env.pkg.shard_rows_weighted(H, rank, self.env.world, self.root_share if balanced else 1.0)
 
-    def frames(self, bvh, cam, W, H, k_steps, d_records, flush=True, timeout_ms=10000):
-        """K frames of rows sharded over the ranks; returns (event0, event1) around them on the main stream."""
+    def frames(self, bvh, cam, W, H, k_steps, d_records, flush=True, timeout_ms=10000, balanced=False):
+        """K frames of rows sharded over the ranks (balanced: with the calibrated shorter band for rank 0); returns
+        (event0, event1) around them on the main stream."""
         env, pkg, torch = self.env, self.env.pkg, self.env.torch
         assert W * H <= self.max_pixels
-        y0, y1 = self.band(H)
+        y0, y1 = self.band(H, balanced)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(k_steps):
@@ -544,7 +545,7 @@ def run_b200(args):
 
     def run_steps(k_steps):
         if dist_on:
-            return gather.frames(bvh, cam, W, H, k_steps, hits_local.data_ptr())
+            return gather.frames(bvh, cam, W, H, k_steps, hits_local.data_ptr(), balanced=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(k_steps):
@@ -561,6 +562,7 @@ def run_b200(args):
         gather.count.zero_()
     clocks = ClockSampler(local)
     clocks.start()
+    env.fence()      # barrier + synchronize directly before the timed steps: the sampler's start-up must not skew the ranks' start
     launches0 = pkg.kernel_launches()
     e0, e1 = run_steps(args.steps)
     env.fence()
@@ -574,7 +576,7 @@ def run_b200(args):
         t_all = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
         dist.all_gather(t_all, torch.tensor([my_ms], dtype=torch.float64, device="cuda"))
         per_rank_ms = [float(t.item()) for t in t_all]
-    fy0, fy1 = gather.band(H) if gather is not None else (y0, y1)       # the band this rank traced in the timed loop
+    fy0, fy1 = gather.band(H, True) if gather is not None else (y0, y1)       # the band this rank traced in the timed loop
     local_hits = int((hits_local[:(fy1 - fy0) * W, 1].view(torch.int32) >= 0).sum().item())
     frame_hits = env.sum_over_ranks(local_hits)
     consumer = None
