@@ -205,7 +205,8 @@ def cpu_reference_run(n_spheres, width, height, fov, row_step, threads, steps=1,
     secs = [run() for _ in range(steps)]
     sec = float(np.mean(secs))
     return {"value": len(rays) / sec / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"SAMPLED: every {row_step}th row of the {width}x{height} primary frame = {len(rays)} rays per step, "
+            "sample": (f"SAMPLED: every {row_step}th row of the" if row_step > 1 else "the WHOLE") +
+                      f" {width}x{height} primary frame = {len(rays)} rays per step, "
                       f"{n_spheres} spheres, ray_bvh_intersect loop only (build {build_s:.1f} s excluded); rate-normalised",
             "seconds_per_step": sec, "rays_per_step": len(rays)}
 

@@ -210,8 +210,8 @@ SAH_HD bool sah_box_exact(const SahRay &r, float lox, float loy, float loz, floa
  * a / t is in 1 +- 2^-22 whenever a and t are normal numbers.  With N = max_a min(a1,a2), F = min_a max(a1,a2):
  *     F (1 - 2^-18) >= max(N, 0)   and   F (1 - 2^-18) > EPSILON
  * imply  tmax >= tmin  and  tmax > EPSILON  for the reference's own t's (the margin is 16x the error bound; values
- * below EPSILON -- the only place denormals could matter -- never take the shortcut, and a NaN or infinite
- * product fails both comparisons).  Anything else, including every zero direction component (r = inf), runs the
+ * below EPSILON -- the only place denormals could matter -- never take the shortcut, a NaN product fails both
+ * comparisons and an infinite one is excluded explicitly).  Anything else, including every zero direction component (r = inf), runs the
  * six true divisions.  A would-be winner's chord through its sphere's box is ~1e3 times wider than the margin, so
  * about 99 % of the calls stop after 3 MUFU + 6 FMUL instead of six IEEE division sequences. */
 #if defined(__CUDA_ARCH__)
@@ -226,7 +226,8 @@ SAH_HD bool sah_box_exact_fast(const SahRay &r, float lox, float loy, float loz,
     const float n = fmaxf(fmaxf(fminf(a1x, a2x), fminf(a1y, a2y)), fmaxf(fminf(a1z, a2z), 0.0f));
     const float f = F_MUL(fminf(fminf(fmaxf(a1x, a2x), fmaxf(a1y, a2y)), fmaxf(a1z, a2z)), 0.999996185302734375f);
     const bool finite = fabsf(rx) <= 3.0e38f && fabsf(ry) <= 3.0e38f && fabsf(rz) <= 3.0e38f;   /* no zero / denormal direction axis */
-    if (finite && f >= n && f > SAH_EPSILON) return true;
+    /* f < 3e38: an overflowed product (inf >= inf would pass) never takes the shortcut either */
+    if (finite && f >= n && f > SAH_EPSILON && f < 3.0e38f) return true;
     return sah_box_exact(r, lox, loy, loz, hix, hiy, hiz);
 }
 #else
