@@ -113,6 +113,17 @@ def test_fuzz_gpu(pkg, oracle, seed, n):
             for pmode in (gpu.PRIMARY_PACKET, gpu.PRIMARY_PER_RAY):
                 gpu.set_primary_mode(pmode)
                 assert_hits_equal(bvh.trace_primary(cam, 320, 200), prim_want, f"fuzz seed {seed} n {n} primary mode {pmode}")
+            # compact outputs: the ids are the records' ids, {t, prim} the records' t, and the records derived from
+            # the ids on demand are the reference's records
+            gpu.set_ray_mode(gpu.RAYS_WIDE)
+            gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+            assert same(bvh.trace_closest_hit_prims(rays), want["prim"])
+            ids = bvh.trace_primary_prims(cam, 320, 200)
+            assert same(ids, prim_want["prim"])
+            tp = bvh.trace_primary_tprim(cam, 320, 200)
+            assert same(tp["prim"], prim_want["prim"]) and same(tp["t"].view(np.uint32), prim_want["t"].view(np.uint32))
+            assert_hits_equal(bvh.hits_from_prims(cam, 320, 200, ids), prim_want, f"fuzz seed {seed} n {n} records from ids")
+            assert bvh.benchmark_with_bvh(rays) == int((want["prim"] >= 0).sum())
             bvh.close()
     finally:
         gpu.set_build_mode(gpu.BUILD_DEVICE)
