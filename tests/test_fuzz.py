@@ -102,6 +102,7 @@ def test_fuzz_gpu(pkg, oracle, seed, n):
     cam["position"] = tuple(float(v) for v in (so["c"][:n].mean(axis=0) + np.array([0.0, 0.0, 3.0 * (np.abs(so["c"][:n]).max() + 1)])))
     prim_want, _ = oracle.trace_bvh(nodes, so, n, oracle.primary_rays(cam, 320, 200))
     try:
+        gpu.set_keep_binary_tree(True)      # the selectable binary-tree kernels are fuzzed too
         for build_mode in (gpu.BUILD_HOST, gpu.BUILD_DEVICE):
             gpu.set_build_mode(build_mode)
             sb = s.copy()
@@ -126,6 +127,7 @@ def test_fuzz_gpu(pkg, oracle, seed, n):
             assert bvh.benchmark_with_bvh(rays) == int((want["prim"] >= 0).sum())
             bvh.close()
     finally:
+        gpu.set_keep_binary_tree(False)
         gpu.set_build_mode(gpu.BUILD_DEVICE)
         gpu.set_ray_mode(gpu.RAYS_WIDE)
         gpu.set_primary_mode(gpu.PRIMARY_PACKET)

@@ -17,8 +17,16 @@ pytestmark = pytest.mark.gpu
 def gpu(pkg):
     if pkg.device_count() < 1:
         pytest.fail("no CUDA device: the closest-hit path has no CPU fallback")
-    pkg.set_keep_binary_tree(True)   # this module switches to the binary-tree kernels on its handles (tests/test_gpu_round2.py runs the default)
     return pkg
+
+
+@pytest.fixture(autouse=True)
+def _keep_binary_tree(pkg):
+    """this module switches to the binary-tree kernels on its handles (tests/test_gpu_round2.py runs the default);
+    set per test, so the result does not depend on which module's tests ran before"""
+    if pkg.device_count() >= 1:
+        pkg.set_keep_binary_tree(True)
+    yield
 
 
 # ---------------------------------------------------------------- config 2: default renderer scene

@@ -28,9 +28,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def gpu(pkg):
     if pkg.device_count() < 1:
         pytest.fail("no CUDA device: the closest-hit path has no CPU fallback")
-    pkg.set_keep_binary_tree(False)      # the product default: handles hold only what the default kernels read
     yield pkg
-    pkg.set_keep_binary_tree(False)
+
+
+@pytest.fixture(autouse=True)
+def _default_handles(pkg):
+    """the product default, set per test (not per module: other modules' tests may run in between): handles hold only
+    what the default kernels read"""
+    if pkg.device_count() >= 1:
+        pkg.set_keep_binary_tree(False)
+    yield
+    if pkg.device_count() >= 1:
+        pkg.set_keep_binary_tree(False)
 
 
 @pytest.fixture(scope="module")
