@@ -130,3 +130,18 @@ class HostEmul:
         out = np.zeros((y1 - y0) * w, RAY_DT)
         self.lib.emul_primary_rays(_ptr(cam), C.c_int(w), C.c_int(h), C.c_int(y0), C.c_int(y1), _ptr(out))
         return out
+
+
+# The library's "keep the 64-byte binary tree in new handles" switch is process-wide and has no getter; the GPU test
+# modules want different values and pytest may interleave them (session-scoped parametrised fixtures reorder tests),
+# so every change goes through here and a module can restore what it found.
+_KEEP_BINARY = [False]
+
+
+def set_keep_binary(pkg, keep):
+    pkg.set_keep_binary_tree(bool(keep))
+    _KEEP_BINARY[0] = bool(keep)
+
+
+def keep_binary_state():
+    return _KEEP_BINARY[0]

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from common import RAY_DT, SPHERE_DT, assert_hits_equal, same
+from common import RAY_DT, SPHERE_DT, assert_hits_equal, keep_binary_state, same, set_keep_binary
 
 
 def odd_scene(rng, n):
@@ -101,8 +101,9 @@ def test_fuzz_gpu(pkg, oracle, seed, n):
     cam = gpu.default_camera()
     cam["position"] = tuple(float(v) for v in (so["c"][:n].mean(axis=0) + np.array([0.0, 0.0, 3.0 * (np.abs(so["c"][:n]).max() + 1)])))
     prim_want, _ = oracle.trace_bvh(nodes, so, n, oracle.primary_rays(cam, 320, 200))
+    keep_before = keep_binary_state()
     try:
-        gpu.set_keep_binary_tree(True)      # the selectable binary-tree kernels are fuzzed too
+        set_keep_binary(gpu, True)          # the selectable binary-tree kernels are fuzzed too
         for build_mode in (gpu.BUILD_HOST, gpu.BUILD_DEVICE):
             gpu.set_build_mode(build_mode)
             sb = s.copy()
@@ -127,7 +128,7 @@ def test_fuzz_gpu(pkg, oracle, seed, n):
             assert bvh.benchmark_with_bvh(rays) == int((want["prim"] >= 0).sum())
             bvh.close()
     finally:
-        gpu.set_keep_binary_tree(False)
+        set_keep_binary(gpu, keep_before)
         gpu.set_build_mode(gpu.BUILD_DEVICE)
         gpu.set_ray_mode(gpu.RAYS_WIDE)
         gpu.set_primary_mode(gpu.PRIMARY_PACKET)

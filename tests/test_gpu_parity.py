@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import HIT_DT, RAY_DT, SPHERE_DT, _ptr, assert_hits_equal, same, sha
+from common import set_keep_binary, HIT_DT, RAY_DT, SPHERE_DT, _ptr, assert_hits_equal, same, sha
 
 pytestmark = pytest.mark.gpu
 
@@ -17,15 +17,15 @@ pytestmark = pytest.mark.gpu
 def gpu(pkg):
     if pkg.device_count() < 1:
         pytest.fail("no CUDA device: the closest-hit path has no CPU fallback")
+    set_keep_binary(pkg, True)   # this module switches to the binary-tree kernels on its handles (tests/test_gpu_round2.py runs the default)
     return pkg
 
 
 @pytest.fixture(autouse=True)
-def _keep_binary_tree(pkg):
-    """this module switches to the binary-tree kernels on its handles (tests/test_gpu_round2.py runs the default);
-    set per test, so the result does not depend on which module's tests ran before"""
-    if pkg.device_count() >= 1:
-        pkg.set_keep_binary_tree(True)
+def _keep_binary_tree(gpu):
+    """again per test: tests of other modules may run between this module's (pytest reorders around session-scoped
+    parametrised fixtures); module-scoped handles of this file depend on `gpu`, which sets it at module set-up"""
+    set_keep_binary(gpu, True)
     yield
 
 

@@ -18,7 +18,7 @@ import time
 import numpy as np
 import pytest
 
-from common import HIT_DT, RAY_DT, assert_hits_equal, same, sha
+from common import set_keep_binary, HIT_DT, RAY_DT, assert_hits_equal, same, sha
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -28,18 +28,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def gpu(pkg):
     if pkg.device_count() < 1:
         pytest.fail("no CUDA device: the closest-hit path has no CPU fallback")
+    set_keep_binary(pkg, False)          # the product default: handles hold only what the default kernels read
     yield pkg
+    set_keep_binary(pkg, False)
 
 
 @pytest.fixture(autouse=True)
-def _default_handles(pkg):
-    """the product default, set per test (not per module: other modules' tests may run in between): handles hold only
-    what the default kernels read"""
-    if pkg.device_count() >= 1:
-        pkg.set_keep_binary_tree(False)
+def _default_handles(gpu):
+    """again per test (other modules' tests may run in between)"""
+    set_keep_binary(gpu, False)
     yield
-    if pkg.device_count() >= 1:
-        pkg.set_keep_binary_tree(False)
+    set_keep_binary(gpu, False)
 
 
 @pytest.fixture(scope="module")
@@ -145,7 +144,7 @@ def test_packet_stack_on_deep_trees_and_coarse_frames(gpu, oracle, kind):
     its widest frontier.  On deep trees (binary depth 40-62) the unchecked pushes used to be able to run past the
     512-entry stack; sahbvh_packet_dfs_from now derives the DFS threshold from the tree depth.  Checked against
     the per-ray kernel (and the oracle where it can build the tree)."""
-    gpu.set_keep_binary_tree(True)
+    set_keep_binary(gpu, True)
     try:
         nodes = None
         if kind == "random5000":
@@ -181,7 +180,7 @@ def test_packet_stack_on_deep_trees_and_coarse_frames(gpu, oracle, kind):
         bvh.close()
     finally:
         gpu.set_primary_mode(gpu.PRIMARY_PACKET)
-        gpu.set_keep_binary_tree(False)
+        set_keep_binary(gpu, False)
 
 
 def test_packet_stack_bound_and_forced_dfs_mode(gpu, oracle, scene100k):
@@ -374,7 +373,7 @@ def test_count_prims_dev_alignment_and_tails(gpu):
 def test_1m_4k_full_frame_kernels_agree_and_oracle_sample(gpu, oracle):
     """The headline workload itself: 1 M spheres, 3840 x 2160.  packet == per-ray == ray-buffer kernel over the
     FULL frame (8.3 M records, bit-exact), ids-only == records, and 200 K pixels against the oracle."""
-    gpu.set_keep_binary_tree(True)
+    set_keep_binary(gpu, True)
     try:
         n, W, H = 1_000_000, 3840, 2160
         oracle.srand(1)
@@ -412,7 +411,7 @@ def test_1m_4k_full_frame_kernels_agree_and_oracle_sample(gpu, oracle):
         bvh.close()
     finally:
         gpu.set_primary_mode(gpu.PRIMARY_PACKET)
-        gpu.set_keep_binary_tree(False)
+        set_keep_binary(gpu, False)
 
 
 # ---------------------------------------------------------------- 10 M spheres, pinned by the reference
