@@ -352,7 +352,7 @@ class FrameGather:
         world, rank, local = env.world, env.rank, env.local
         handles = [None] * 4
         owned = None
-        ok = 1
+        ok = 0 if os.environ.get("SAHBVH_BENCH_NO_IPC") else 1      # test hook: exercise the no-assembly fallback
         try:
             if rank == 0:
                 owned = [pkg.peer_alloc(max_pixels * 4, local) for _ in range(2)] + [pkg.peer_alloc(8 * (world + 1), local),
@@ -483,6 +483,15 @@ class FrameGather:
 
     def close(self):
         env = self.env
+        if not self.ok:
+            # set-up failed on some rank: every rank knows (ok is all-reduced); release what this rank holds, no barriers
+            for p in (self.ptrs or []):
+                try:
+                    (env.pkg.peer_free if env.rank == 0 else env.pkg.peer_close)(p, env.local)
+                except Exception:
+                    pass
+            self.ptrs = None
+            return
         if not self.ptrs:
             return
         env.torch.cuda.synchronize()
@@ -542,10 +551,16 @@ def run_b200(args):
     if dist_on:
         gather = FrameGather(env, max(total_rays, 7680 * 4320))
         if not gather.ok:
-            raise SystemExit("bench.py: CUDA IPC peer mapping of the frame buffer is unavailable on this box")
+            # no CUDA IPC peer mapping on this box: the bands are still traced and timed, but nothing assembles or
+            # consumes the frame; the line says so (config.parallelism, frame_consumer) instead of losing the run
+            if rank == 0:
+                print("bench.py: CUDA IPC peer mapping of the frame buffer is unavailable; timing the bands without frame assembly", file=sys.stderr)
+            gather.close()
+            gather = None
+    assembled = gather is not None
 
     def run_steps(k_steps):
-        if dist_on:
+        if assembled:
             return gather.frames(bvh, cam, W, H, k_steps, hits_local.data_ptr(), balanced=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -581,7 +596,9 @@ def run_b200(args):
     local_hits = int((hits_local[:(fy1 - fy0) * W, 1].view(torch.int32) >= 0).sum().item())
     frame_hits = env.sum_over_ranks(local_hits)
     consumer = None
-    if dist_on:
+    if dist_on and not assembled:
+        consumer = {"what": "NOT RUN: no CUDA IPC peer mapping on this box, the bands were traced without frame assembly", "ok": None}
+    if assembled:
         consumed_total = int(gather.count.item()) if rank == 0 else 0
         consumer = {"what": "rank 0 consumes every assembled frame inside the timed loop: device-side wait for all bands' flags, hit "
                             "count over the frame's ids (benchmark.c:242-244), 'consumed' flag; producers wait for it before "
@@ -635,7 +652,7 @@ def run_b200(args):
 
     # ---- N > 1: extra rows (all ranks take part; rank 0 reports)
     multi_rows = []
-    if dist_on and not args.no_sweep:
+    if assembled and not args.no_sweep:
         multi_rows = run_multi_rows(env, gather, bvh, spheres, hits_local)
 
     if rank != 0:
@@ -745,7 +762,8 @@ def run_b200(args):
                                   (", frame assembly fused into the trace kernel: every rank stores its band's 4-byte primitive ids straight "
                                    "into rank 0's frame buffer over NVLink peer memory (CUDA IPC mapping) as 128-byte row segments and a "
                                    "completion flag behind it; rank 0 consumes every frame and the ranks wait for its 'consumed' flag "
-                                   "before reusing a buffer; no collective inside the frame loop" if dist_on else "")},
+                                   "before reusing a buffer; no collective inside the frame loop" if assembled else
+                                   (", NO frame assembly (CUDA IPC peer mapping unavailable on this box)" if dist_on else ""))},
         "clocks": clk,
         "e2e": e2e,
         "e2e_variants": e2e_variants,
