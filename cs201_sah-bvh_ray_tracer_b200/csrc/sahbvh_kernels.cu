@@ -1427,6 +1427,24 @@ extern "C" int gpu_trace_closest_hit_dev(gpu_bvh *b, const void *d_rays, int64_t
     return sahbvh_launch_rays(b, d_rays, n, d_out, (cudaStream_t)stream, false);
 }
 
+/* error exit of a host-buffer call whose earlier chunks may still be copying from / into the caller's arrays: let
+ * them finish before the error returns (the caller may free the arrays right away) */
+static int fail_after_drain(gpu_bvh *b, int rc)
+{
+    cudaStreamSynchronize(b->streams[0]);
+    cudaStreamSynchronize(b->streams[1]);
+    (void)cudaGetLastError();
+    return rc;
+}
+#define CU_TRY_DRAIN(b, expr)                                                                     \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            sahbvh_set_error("%s failed: %s (%s:%d)", #expr, cu_errstr(_e), __FILE__, __LINE__); \
+            return fail_after_drain((b), SAHBVH_E_CUDA);                                          \
+        }                                                                                         \
+    } while (0)
+
 static int trace_rays_host(gpu_bvh *b, const Ray *rays, int64_t n, void *out, bool prims_only)
 {
     if (!b || n < 0 || (n > 0 && (!rays || !out))) {
@@ -1443,11 +1461,11 @@ static int trace_rays_host(gpu_bvh *b, const Ray *rays, int64_t n, void *out, bo
     for (long long off = 0; off < n; off += chunk, k ^= 1) {
         long long m = n - off < chunk ? n - off : chunk;
         cudaStream_t st = b->streams[k];
-        CU_TRY(cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
+        CU_TRY_DRAIN(b, cudaMemcpyAsync(b->d_in[k], rays + off, (size_t)m * sizeof(Ray), cudaMemcpyHostToDevice, st));
         rc = prims_only ? sahbvh_launch_rays(b, b->d_in[k], m, nullptr, st, false, b->d_out[k])
                         : sahbvh_launch_rays(b, b->d_in[k], m, b->d_out[k], st, false);
-        if (rc != SAHBVH_OK) return rc;
-        CU_TRY(cudaMemcpyAsync((char *)out + (size_t)off * rec, b->d_out[k], (size_t)m * rec, cudaMemcpyDeviceToHost, st));
+        if (rc != SAHBVH_OK) return fail_after_drain(b, rc);
+        CU_TRY_DRAIN(b, cudaMemcpyAsync((char *)out + (size_t)off * rec, b->d_out[k], (size_t)m * rec, cudaMemcpyDeviceToHost, st));
         /* the staging pair k is reused two chunks later: the stream orders it */
     }
     CU_TRY(cudaStreamSynchronize(b->streams[0]));
@@ -1609,9 +1627,15 @@ int sahbvh_primary_host_enqueue(gpu_bvh *b, const Camera *cam, int width, int he
         cudaStream_t st = b->streams[k];
         if (fmt == HOSTFMT_RECORDS) rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, b->d_out[k], st, false, nullptr, SAH_IDS_NONE);
         else rc = sahbvh_launch_primary(b, cam, width, height, ya, yb, nullptr, st, false, b->d_out[k], ids_mode);
-        if (rc != SAHBVH_OK) return rc;
-        CU_TRY(cudaMemcpyAsync((char *)out + (size_t)(ya - y0) * (size_t)width * px_bytes, b->d_out[k],
-                               (size_t)(yb - ya) * (size_t)width * px_bytes, cudaMemcpyDeviceToHost, st));
+        if (rc == SAHBVH_OK) {
+            const cudaError_t e = cudaMemcpyAsync((char *)out + (size_t)(ya - y0) * (size_t)width * px_bytes, b->d_out[k],
+                                                  (size_t)(yb - ya) * (size_t)width * px_bytes, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) {
+                sahbvh_set_error("gpu_trace_primary: copy to the host buffer failed: %s", cu_errstr(e));
+                rc = SAHBVH_E_CUDA;
+            }
+        }
+        if (rc != SAHBVH_OK) return fail_after_drain(b, rc);
     }
     return SAHBVH_OK;
 }
@@ -1668,10 +1692,10 @@ extern "C" int gpu_hits_from_prims(gpu_bvh *b, const Camera *cam, int width, int
         const int yb = ya + band < y1 ? ya + band : y1;
         const size_t off = (size_t)(ya - y0) * (size_t)width, npx = (size_t)(yb - ya) * (size_t)width;
         cudaStream_t st = b->streams[k];
-        CU_TRY(cudaMemcpyAsync(b->d_in[k], prims + off, npx * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY_DRAIN(b, cudaMemcpyAsync(b->d_in[k], prims + off, npx * 4, cudaMemcpyHostToDevice, st));
         rc = gpu_hits_from_prims_dev(b, cam, width, height, ya, yb, b->d_in[k], b->d_out[k], st);
-        if (rc != SAHBVH_OK) return rc;
-        CU_TRY(cudaMemcpyAsync(out + off, b->d_out[k], npx * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
+        if (rc != SAHBVH_OK) return fail_after_drain(b, rc);
+        CU_TRY_DRAIN(b, cudaMemcpyAsync(out + off, b->d_out[k], npx * sizeof(gpu_hit), cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaStreamSynchronize(b->streams[0]));
     CU_TRY(cudaStreamSynchronize(b->streams[1]));
