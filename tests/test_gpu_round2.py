@@ -353,6 +353,27 @@ def test_peer_wait_and_signal_on_one_device(gpu):
     assert int(status.item()) == 1
 
 
+def test_l2_persisting_window_option_changes_nothing_but_residency(gpu, oracle, scene100k):
+    """sahbvh_set_l2_persist_bytes: trace launches run with an access-policy window over the top of the breadth-first
+    node array; records stay bit-identical, and switching it off again restores the default launches."""
+    bvh, so, nodes = scene100k
+    n = 100000
+    oracle.srand(5)
+    rays = oracle.rays_benchmark(30000)
+    want, _ = oracle.trace_bvh(nodes, so, n, rays)
+    cam = gpu.default_camera()
+    try:
+        base_prim = bvh.trace_primary_prims(cam, 640, 360)
+        for mb in (1, 64, 4096):                                   # smaller, about equal to and far larger than the tree
+            gpu.set_l2_persist_bytes(mb << 20)
+            assert_hits_equal(bvh.trace_closest_hit(rays), want, f"L2 window {mb} MiB")
+            assert same(bvh.trace_primary_prims(cam, 640, 360), base_prim)
+        gpu.set_l2_persist_bytes(0)
+        assert_hits_equal(bvh.trace_closest_hit(rays), want, "L2 window off again")
+    finally:
+        gpu.set_l2_persist_bytes(0)
+
+
 def test_count_prims_dev_alignment_and_tails(gpu):
     """gpu_count_prims_dev (the frame consumer's reduction) reads 128-bit words: unaligned starts, short arrays and
     tails must count exactly like benchmark.c:242-244's loop."""
