@@ -353,6 +353,28 @@ def test_peer_wait_and_signal_on_one_device(gpu):
     assert int(status.item()) == 1
 
 
+def test_random_cameras_and_odd_frames(gpu, oracle, scene100k):
+    """The packet kernel's tile frusta depend on the camera: positions inside and outside the scene, every yaw / pitch
+    quadrant (axis-aligned views put zero direction components on whole pixel rows and columns), narrow and wide
+    fields of view, frames from one pixel to ragged non-multiples of the 16 x 8 tile -- records equal the oracle's."""
+    bvh, s, nodes = scene100k
+    rng = np.random.default_rng(2024)
+    cams = []
+    for k in range(7):
+        cam = oracle.default_camera()
+        cam["position"] = tuple(float(v) for v in (rng.uniform(-600, 600, 3) if k % 2 else rng.uniform(-80, 80, 3)))
+        cam["yaw"] = np.float32([0.0, np.pi / 2, -np.pi, 1.0, -2.5, 0.3, 3.0][k])
+        cam["pitch"] = np.float32([0.0, 0.0, 0.7, -1.2, 0.05, 1.5, -0.4][k])
+        cam["fov"] = np.float32([45.0, 90.0, 5.0, 120.0, 60.0, 30.0, 170.0][k])
+        cams.append(oracle.camera_update(cam))
+    sizes = [(333, 211), (64, 40), (1, 1), (15, 7), (17, 130)]
+    for k, cam in enumerate(cams):
+        for W, H in sizes[k % 2::2] if k else sizes:
+            want, _ = oracle.trace_bvh(nodes, s, 100000, oracle.primary_rays(cam, W, H))
+            assert_hits_equal(bvh.trace_primary(cam, W, H), want, f"camera {k} frame {W}x{H}")
+            assert same(bvh.trace_primary_prims(cam, W, H), want["prim"])
+
+
 def test_l2_persisting_window_option_changes_nothing_but_residency(gpu, oracle, scene100k):
     """sahbvh_set_l2_persist_bytes: trace launches run with an access-policy window over the top of the breadth-first
     node array; records stay bit-identical, and switching it off again restores the default launches."""
