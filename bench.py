@@ -264,6 +264,21 @@ def wall(fn, reps, warm=2):
     return (time.perf_counter() - t0) / reps
 
 
+KERNEL_NAMES = {0: "k_trace_primary", 1: "k_trace_primary_packet", 2: "k_trace_primary_macro"}
+
+
+def settle_primary(torch, bvh, cam, W, H, y0, y1, d_out, stream, max_launches=24):
+    """SAHBVH_PRIMARY_AUTO samples both packet kernels on the first launches of a frame shape; a steady-state measurement
+    starts after the handle has settled.  Returns the kernel id in use (1 = 16x8 tiles, 2 = 32x8 macro tiles)."""
+    for _ in range(max_launches):
+        k = bvh.primary_kernel_in_use(W, y1 - y0)
+        if k >= 0:
+            return k
+        bvh.trace_primary_dev(cam, W, H, y0, y1, d_out, stream)
+        torch.cuda.synchronize()
+    return bvh.primary_kernel_in_use(W, y1 - y0)
+
+
 def algorithmic(stats, generated, with_input):
     """bytes/ray = 64 V_i + 16 V_s + B_in + 32 ; FLOP/ray = 48 V_i + 25 V_s + 23 [hit] + 26 [generated]."""
     rays = max(stats["rays"], 1)
@@ -570,8 +585,11 @@ def run_b200(args):
         e1.record()
         return e0, e1
 
+    kernel_id = settle_primary(torch, bvh, cam, W, H, y0, y1, hits_local.data_ptr(), stream)
     if gather is not None:
         gather.calibrate(bvh, cam, W, H, hits_local.data_ptr())
+        by0, by1 = gather.band(H, True)
+        settle_primary(torch, bvh, cam, W, H, by0, by1, hits_local.data_ptr(), stream)
     run_steps(args.warmup)
     env.fence()
     if gather is not None:
@@ -672,21 +690,24 @@ def run_b200(args):
     pkg.set_keep_binary_tree(False)
     pkg.set_primary_mode(pkg.PRIMARY_PER_RAY)
     stats_ray = bvh_bin.trace_primary_stats(cam, W, H, y0, y1, hits_local.data_ptr())
-    pkg.set_primary_mode(pkg.PRIMARY_PACKET)
+    pkg.set_primary_mode(pkg.PRIMARY_DEFAULT)
     bvh_bin.close()
     model = algorithmic(stats_ray, generated=True, with_input=False)      # SURVEY 8(d) per-ray figure
     peaks = pkg.measure_peaks(local)
     k_s = k_ms * 1e-3
     compulsory_bytes = 32 * n_local + info["n_wide"] * 128 + (info["n_spheres"] + 1) * 16
     touched_bytes = 128 * stats["inner_visits"] + 16 * stats["sphere_tests"] + 32 * n_local   # 128-byte 4-wide nodes
-    rec = traffic_record("k_trace_primary_packet", W, rows, args.spheres) if world == 1 else None
+    kernel_id = bvh.primary_kernel_in_use(W, rows) if bvh.primary_kernel_in_use(W, rows) >= 0 else kernel_id
+    kname = KERNEL_NAMES.get(kernel_id, "k_trace_primary_packet")
+    tiles = ((W + 31) // 32) * ((rows + 7) // 8) if kernel_id == 2 else tiles     # macro tiles of 32 x 8 pixels
+    rec = traffic_record(kname, W, rows, args.spheres) if world == 1 else None
     scaled_from = None
     if rec is None and args.spheres == N_SPHERES:
         # N > 1 (or another frame of the same scene): the weak-scaled frame keeps the pixel pitch, so a band's tiles do the
         # same work as the headline frame's; the instruction count is the headline capture scaled by the tile count
-        base = traffic_record("k_trace_primary_packet", WIDTH, HEIGHT, N_SPHERES)
+        base = traffic_record(kname, WIDTH, HEIGHT, N_SPHERES)
         if base and base.get("warp_inst_per_launch"):
-            base_tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 7) // 8)
+            base_tiles = (((WIDTH + 31) // 32) if kernel_id == 2 else ((WIDTH + 15) // 16)) * ((HEIGHT + 7) // 8)
             rec = dict(base)
             rec["warp_inst_per_launch"] = base["warp_inst_per_launch"] * tiles / base_tiles
             rec["dram_bytes_per_launch"] = None
@@ -696,7 +717,7 @@ def run_b200(args):
     if rec and rec.get("warp_inst_per_launch"):
         inst = float(rec["warp_inst_per_launch"])
         roofline = {
-            "kernel": "k_trace_primary_packet", "bound": "fp32_issue",
+            "kernel": kname, "bound": "fp32_issue",
             "achieved": inst / k_s / 1e9, "peak": slots / 1e9, "unit": "G warp-inst/s", "frac": inst / k_s / slots,
             "traffic": rec.get("dram_bytes_per_launch"),
             "traffic_note": "static: ncu dram__bytes_read+write of one launch of this configuration, captured WITHOUT the L2 "
@@ -712,7 +733,7 @@ def run_b200(args):
             roofline["traffic_note"] = "no DRAM capture for this frame size"
     else:
         roofline = {
-            "kernel": "k_trace_primary_packet", "bound": "hbm",
+            "kernel": kname, "bound": "hbm",
             "achieved": compulsory_bytes / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": compulsory_bytes / k_s / 1e9 / hbm_peak,
             "traffic": None,
             "what": "no ncu instruction count is recorded for this configuration (profiles/ncu_traffic.json holds the headline "
@@ -722,7 +743,8 @@ def run_b200(args):
         "hbm_compulsory_frac": compulsory_bytes / k_s / 1e9 / hbm_peak, "hbm_compulsory_bytes_per_launch": compulsory_bytes,
         "l2_touched_frac": touched_bytes / k_s / 1e9 / peaks["l2_read_gbs"] if peaks["l2_read_gbs"] else None,
         "l2_touched_bytes_per_launch": touched_bytes, "l2_read_peak_gbs": peaks["l2_read_gbs"],
-        "tile_work": {"tiles": tiles, "nodes_popped_per_tile": stats["inner_visits"] / tiles,
+        "tile_work": {"tile": "32x8-pixel macro tile (two 16x8 sub-tiles)" if kernel_id == 2 else "16x8-pixel tile",
+                      "tiles": tiles, "nodes_popped_per_tile": stats["inner_visits"] / tiles,
                       "sphere_tests_per_ray": stats["sphere_tests"] / n_local,
                       "exact_leaf_box_tests_per_ray": stats["exact_box_tests"] / n_local, "max_stack": stats["max_stack"]},
         "survey_8d_per_ray_model": {
@@ -805,6 +827,7 @@ def run_multi_rows(env, gather, bvh1m, spheres1m, hits_local):
     y0, y1 = pkg.shard_rows(H, rank, world)
 
     def strong_row(n, bvh):
+        settle_primary(torch, bvh, cam, W, H, y0, y1, hits_local.data_ptr(), stream)
         gather.frames(bvh, cam, W, H, warm, hits_local.data_ptr())
         env.fence()
         gather.count.zero_()
@@ -932,6 +955,7 @@ def config5_multi(env, gather):
     ms = env.max_over_ranks(e0.elapsed_time(e1)) / frames
     # primary-only rate of the same tree and frame (closest-hit Grays/s at 10 M spheres)
     hits = torch.empty((npx, 8), dtype=torch.float32, device="cuda")
+    settle_primary(torch, bvh, cam, W, H, y0, y1, hits.data_ptr(), stream)
     pms = env.max_over_ranks(time_steps(torch, lambda: bvh.trace_primary_dev(cam, W, H, y0, y1, hits.data_ptr(), stream), 5, 2, env.flush)[0] / 5)
     info = bvh.info()
     bvh.close()
@@ -960,17 +984,19 @@ def run_sweep(env, bvh1m, spheres1m, peaks, clk):
     def primary_row(name, bvh, W, H, n):
         buf = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
         fn = lambda: bvh.trace_primary_dev(cam, W, H, 0, H, buf.data_ptr(), stream)
+        kid = settle_primary(torch, bvh, cam, W, H, 0, H, buf.data_ptr(), stream)
         total_ms, _ = time_steps(torch, fn, steps, warm, env.flush)
         ms = total_ms / steps
         st = bvh.trace_primary_stats(cam, W, H, 0, H, buf.data_ptr())
         info = bvh.info()
-        tiles = ((W + 15) // 16) * ((H + 7) // 8)
+        tiles = (((W + 31) // 32) if kid == 2 else ((W + 15) // 16)) * ((H + 7) // 8)
         touched = 128 * st["inner_visits"] + 16 * st["sphere_tests"] + 32 * W * H
         compulsory = 32 * W * H + info["n_wide"] * 128 + (info["n_spheres"] + 1) * 16
         h_ids = torch.empty((W * H,), dtype=torch.int32).pin_memory()
         sec = wall(lambda: bvh.trace_primary_prims_ptr(cam, W, H, 0, H, h_ids.data_ptr()), steps)
         out.append({"workload": name, "n_spheres": n, "rays": W * H, "ms_per_step": ms, "value": W * H / (ms * 1e-3) / 1e9, "unit": UNIT,
-                    "kernel": "k_trace_primary_packet (one warp per 16x8-pixel tile: the work is per TILE, not per ray)",
+                    "kernel": KERNEL_NAMES.get(kid, "?") + (" (one warp per 32x8-pixel macro tile" if kid == 2 else " (one warp per 16x8-pixel tile") +
+                              ": the work is per TILE, not per ray; picked by SAHBVH_PRIMARY_AUTO)",
                     "per_tile": {"tiles": tiles, "wide_nodes_popped": st["inner_visits"] / tiles, "sphere_tests_per_ray": st["sphere_tests"] / (W * H),
                                  "hit_rate": st["hits"] / (W * H)},
                     "l2_touched_frac": touched / (ms * 1e-3) / 1e9 / peaks["l2_read_gbs"] if peaks["l2_read_gbs"] else None,

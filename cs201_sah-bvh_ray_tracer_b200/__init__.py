@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "gpu_trace_primary_dev_prims", "gpu_hits_from_prims_dev", "gpu_render_frame", "gpu_render_frame_dev", "gpu_accumulate", "gpu_accumulate_dev", "sahbvh_write_ppm",
     "sahbvh_host_alloc", "sahbvh_host_free", "sahbvh_host_pin", "sahbvh_host_unpin",
     "gpu_trace_closest_hit_prims", "gpu_trace_closest_hit_dev_prims", "gpu_trace_primary_prims", "gpu_trace_primary_tprim",
-    "gpu_hits_from_prims", "sahbvh_set_keep_binary_tree", "sahbvh_set_l2_persist_bytes", "sahbvh_peer_wait", "gpu_count_prims_dev",
+    "gpu_hits_from_prims", "gpu_primary_kernel_in_use", "sahbvh_set_keep_binary_tree", "sahbvh_set_l2_persist_bytes", "sahbvh_peer_wait", "gpu_count_prims_dev",
     "gpu_bvh_replicate", "gpu_bvh_build_replicated", "gpu_bvh_set_free", "gpu_bvh_set_size", "gpu_bvh_set_get",
     "sahbvh_shard_range", "sahbvh_shard_rows", "sahbvh_shard_rows_weighted", "gpu_trace_primary_multi", "gpu_trace_primary_prims_multi",
     "gpu_trace_primary_prims_multi_dev", "gpu_trace_closest_hit_multi", "gpu_trace_closest_hit_prims_multi",
@@ -132,7 +132,8 @@ def measure_peaks(device: int = -1) -> dict:
     return {k: float(getattr(p, k)) for k, _ in p._fields_}
 
 
-PRIMARY_PER_RAY, PRIMARY_PACKET = 0, 1
+PRIMARY_PER_RAY, PRIMARY_PACKET, PRIMARY_MACRO, PRIMARY_AUTO = 0, 1, 2, 3
+PRIMARY_DEFAULT = PRIMARY_AUTO
 
 
 RAYS_ONE_SHOT, RAYS_COOP, RAYS_WIDE = 0, 1, 2
@@ -452,6 +453,10 @@ class GpuBvh:
         _check(lib.gpu_hits_from_prims_dev(self._h, _ptr(cam), C.c_int(width), C.c_int(height), C.c_int(y0), C.c_int(y1),
                                            C.c_void_p(d_prims), C.c_void_p(d_out), C.c_void_p(stream)),
                "gpu_hits_from_prims_dev")
+
+    def primary_kernel_in_use(self, width: int, rows: int) -> int:
+        """PRIMARY_* id of the kernel this handle uses for frames of this shape; -1 while PRIMARY_AUTO is sampling"""
+        return int(lib.gpu_primary_kernel_in_use(self._h, C.c_int(width), C.c_int(rows)))
 
     def trace_closest_hit_stats(self, d_rays: int, n: int, d_out: int) -> dict:
         st = TraceStats()

@@ -9,6 +9,15 @@
 #include "sahbvh_internal.h"
 #include "traverse_core.cuh"
 
+/* SAHBVH_PRIMARY_AUTO: per frame shape, which of the two packet kernels is faster on this handle (sahbvh_kernels.cu) */
+#define SAHBVH_TUNE_SLOTS 8
+struct PrimaryTune {
+    int width, rows;          /* key */
+    int decided;              /* -1 while sampling, else SAHBVH_PRIMARY_PACKET / SAHBVH_PRIMARY_MACRO */
+    int launches;
+    cudaEvent_t ev[2][2][2];  /* [kernel][sample][start, stop] */
+};
+
 struct gpu_bvh {
     int device;
     float *d_nodes;
@@ -32,6 +41,9 @@ struct gpu_bvh {
     /* path-loop work buffers (render.cu), one allocation grown on demand */
     void *d_render;
     size_t render_cap;
+    PrimaryTune tune[SAHBVH_TUNE_SLOTS];
+    int n_tune;
+    unsigned tune_evict;
     size_t l2_limit_applied; /* persisting-L2 set-aside this handle asked the device for (sahbvh_set_l2_persist_bytes) */
 };
 

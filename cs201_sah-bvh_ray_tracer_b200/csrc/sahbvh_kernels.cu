@@ -35,7 +35,7 @@ static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 #define PRIMARY_THREADS 256 /* 32 x 8 pixels per CTA, one 8x4 tile per warp */
 
 std::atomic<unsigned long long> g_launches{0};
-static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_PACKET};
+static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_AUTO};
 static std::atomic<int> g_ray_mode{SAHBVH_RAYS_WIDE};
 static std::atomic<int> g_build_mode{SAHBVH_BUILD_DEVICE};
 static std::atomic<int> g_keep_binary{0};
@@ -70,7 +70,7 @@ extern "C" int sahbvh_set_ray_mode(int mode)
 
 extern "C" int sahbvh_set_primary_mode(int mode)
 {
-    if (mode != SAHBVH_PRIMARY_PER_RAY && mode != SAHBVH_PRIMARY_PACKET) return SAHBVH_E_ARG;
+    if (mode != SAHBVH_PRIMARY_PER_RAY && mode != SAHBVH_PRIMARY_PACKET && mode != SAHBVH_PRIMARY_MACRO && mode != SAHBVH_PRIMARY_AUTO) return SAHBVH_E_ARG;
     g_primary_mode.store(mode);
     return SAHBVH_OK;
 }
@@ -477,13 +477,14 @@ extern "C" int sahbvh_set_packet_dfs_from(int v)
     g_pkt_dfs_override.store(v);
     return SAHBVH_OK;
 }
-static int sahbvh_packet_dfs_from(int tree_depth)
+static int sahbvh_packet_dfs_from(int tree_depth, int stack_entries = PKT_STACK)
 {
-    if (g_pkt_dfs_override.load() > 0) return g_pkt_dfs_override.load();
     int d = tree_depth < 1 ? 1 : tree_depth;
     if (d > SAHBVH_STACK_MAX) d = SAHBVH_STACK_MAX;
-    const int v = PKT_STACK - 32 - 3 * (d + 2);
-    return v < 8 ? 8 : v;
+    int v = stack_entries - 32 - 3 * (d + 2);
+    v = v < 8 ? 8 : v;
+    const int forced = g_pkt_dfs_override.load();
+    return forced > 0 && forced < v ? forced : v;   /* the diagnostic override can only lower the threshold */
 }
 static_assert(PKT_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_STACK too small for the deepest admissible tree");
 
@@ -729,6 +730,258 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
                 SahRay ray;
                 ray.ox = cam.px; ray.oy = cam.py; ray.oz = cam.pz;
                 ray.dx = s_ray[w2][k][0][l2]; ray.dy = s_ray[w2][k][1][l2]; ray.dz = s_ray[w2][k][2][l2];
+                const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + bp);
+                sah_finish_hit(ray, bt, bp, s.x, s.y, s.z, h);
+            } else {
+                sah_miss(h);
+            }
+            store_hit256(out + pix, h);
+        }
+        if (COUNT) hits += (bp >= 0);
+    }
+    if (COUNT) flush_counters(cnt, hits, counters);
+}
+
+/*
+ * K2m: packet traversal over MACRO tiles.  One warp owns 32 x (8 SUBY) pixels = S = 2 SUBY sub-tiles of 16 x 8 (the
+ * tile of K2p), i.e. 4 S rays per lane.  The interior culling -- half of K2p's instructions -- runs ONCE per macro
+ * tile against the macro frustum; a candidate leaf is then tested against the S sub-tile frusta (one lane per
+ * sub-tile, one ballot) and only the sub-tiles it can touch run the reference's sphere / leaf-box tests, with their
+ * own cull bound.  Per ray the exact tests are the same as in K2p (best over leaves whose own tests pass), so the
+ * records are identical; what is shared wider is only the conservative culling.
+ * A macro tile is 32 pixels wide, so the warp's own rows are whole 128-byte id rows (1 KiB of records): results
+ * leave through the warp's shared-memory state without a block barrier.
+ */
+#ifndef PKT_MACRO_MIN_BLOCKS
+#define PKT_MACRO_MIN_BLOCKS 8 /* 64 registers (no spills) and 24.5 KB of shared memory per 4-warp block: 32 warps per SM */
+#endif
+#ifndef PKT_MACRO_STACK
+#define PKT_MACRO_STACK 256
+#endif
+static_assert(PKT_MACRO_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_MACRO_STACK too small for the deepest admissible tree");
+#define PKT_MACRO_WARPS(SUBY) (4 / (SUBY)) /* warps per block: 4 x 9 KB of per-warp state at SUBY = 1, 2 x 17 KB at SUBY = 2 */
+struct PktSubFrustum {
+    SahFrustumAxis x, y, z;
+    float best_s; /* the sub-tile's cull bound (max over its rays of best_s) */
+};
+
+template <bool COUNT, bool RECORDS, int SUBY>
+__global__ void __launch_bounds__(PKT_MACRO_WARPS(SUBY) * 32, PKT_MACRO_MIN_BLOCKS)
+k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
+                      SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
+                      int ids_mode, int dfs_from, unsigned long long *counters)
+{
+    constexpr int S = 2 * SUBY;          /* sub-tiles per macro tile: 2 across, SUBY down */
+    constexpr int MW = PKT_MACRO_WARPS(SUBY);
+    constexpr int MROWS = 8 * SUBY;      /* pixel rows of a macro tile */
+    __shared__ int32_t s_stack[MW][PKT_MACRO_STACK];
+    __shared__ float s_ray[MW][S][PKT_K][3][32];   /* dx, dy, dz (d.d is recomputed: shared memory decides the occupancy) */
+    __shared__ float s_bt[MW][S][PKT_K][32];
+    __shared__ int32_t s_bp[MW][S][PKT_K][32];
+    __shared__ PktSubFrustum s_sub[MW][S];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mtiles_x = (width + 31) >> 5, mtiles_y = (y1 - y0 + MROWS - 1) / MROWS;
+    SahCounters cnt = {0, 0, 0, 0};
+    unsigned long long hits = 0;
+    const long long mt = (long long)blockIdx.x * MW + warp;   /* macro tiles in row-major order */
+    if (mt >= (long long)mtiles_x * mtiles_y) return;                      /* no block barrier in this kernel */
+    const int ty = (int)(mt / mtiles_x), tx = (int)(mt % mtiles_x);
+    int32_t *stack = s_stack[warp];
+    /* ---- the lane's 4 S rays: sub-tile q = (qy, qx), ray k as in K2p:
+     *      pixel (tx*32 + qx*16 + (k&1)*8 + lane%8,  y0 + ty*MROWS + qy*8 + (k>>1)*4 + lane/8) ---- */
+    const int px0 = tx * 32 + (lane & 7), py0 = y0 + ty * MROWS + (lane >> 3);
+    unsigned valid = 0; /* bit q*4+k */
+    /* the lane's rays use 4 distinct columns: one division each (main.c:362); the loops below stay ROLLED -- the
+     * IEEE division / square-root sequences of one ray set-up, one sphere test and one leaf-box test are each
+     * instantiated once, which keeps the kernel inside the instruction cache (ncu: no_instruction stalls) */
+    const float u0 = sah_pixel_u(cam, px0), u1 = sah_pixel_u(cam, px0 + 8), u2 = sah_pixel_u(cam, px0 + 16), u3 = sah_pixel_u(cam, px0 + 24);
+    float mminx = INFINITY, mminy = INFINITY, mminz = INFINITY, mmaxx = -INFINITY, mmaxy = -INFINITY, mmaxz = -INFINITY;
+    float mmin_a = INFINITY;
+    float ex = fmaxf(fabsf(cam.px - sc.lo[0]), fabsf(cam.px - sc.hi[0]));
+    float ey = fmaxf(fabsf(cam.py - sc.lo[1]), fabsf(cam.py - sc.hi[1]));
+    float ez = fmaxf(fabsf(cam.pz - sc.lo[2]), fabsf(cam.pz - sc.hi[2]));
+    const float pad = sqrtf(ex * ex + ey * ey + ez * ez) * 0.001953125f + sc.r_max * 0.001953125f;
+    const bool geo = sc.geometric_zero_axes != 0;
+    bool sub_simple_acc = true;
+#pragma unroll 1
+    for (int q = 0; q < S; q++) {
+        const int qx = q & 1, qy = q >> 1;
+        float lminx = INFINITY, lminy = INFINITY, lminz = INFINITY, lmaxx = -INFINITY, lmaxy = -INFINITY, lmaxz = -INFINITY;
+        float lmin_a = INFINITY;
+#pragma unroll 1
+        for (int k = 0; k < PKT_K; k++) {
+            const int px = px0 + qx * 16 + (k & 1) * 8, py = py0 + qy * 8 + (k >> 1) * 4;
+            float dx, dy, dz;
+            const float u = qx ? ((k & 1) ? u3 : u2) : ((k & 1) ? u1 : u0);
+            sah_primary_dir_uv(cam, u, sah_pixel_v(cam, py), dx, dy, dz);
+            const float ra = F_ADD(F_ADD(F_MUL(dx, dx), F_MUL(dy, dy)), F_MUL(dz, dz));
+            s_ray[warp][q][k][0][lane] = dx; s_ray[warp][q][k][1][lane] = dy; s_ray[warp][q][k][2][lane] = dz;
+            s_bt[warp][q][k][lane] = 0.0f;
+            s_bp[warp][q][k][lane] = -1;
+            if (px < width && py < y1) {
+                valid |= 1u << (q * 4 + k);
+                lminx = fminf(lminx, dx); lmaxx = fmaxf(lmaxx, dx);
+                lminy = fminf(lminy, dy); lmaxy = fmaxf(lmaxy, dy);
+                lminz = fminf(lminz, dz); lmaxz = fmaxf(lmaxz, dz);
+                lmin_a = fminf(lmin_a, ra);
+            }
+        }
+        lminx = warp_min(lminx); lminy = warp_min(lminy); lminz = warp_min(lminz);
+        lmaxx = warp_max(lmaxx); lmaxy = warp_max(lmaxy); lmaxz = warp_max(lmaxz);
+        lmin_a = warp_min(lmin_a);
+        PktSubFrustum sf;
+        sah_frustum_axis_setup(sf.x, cam.px, lminx, lmaxx, pad, geo);
+        sah_frustum_axis_setup(sf.y, cam.py, lminy, lmaxy, pad, geo);
+        sah_frustum_axis_setup(sf.z, cam.pz, lminz, lmaxz, pad, geo);
+        /* an empty sub-tile (off the frame) has mode-3 axes, which accept every box: a negative bound keeps it out */
+        sf.best_s = __any_sync(full, (valid >> (q * 4)) & 15u) ? INFINITY : -1.0f;
+        if (lane == 0) s_sub[warp][q] = sf;
+        sub_simple_acc = sub_simple_acc && (sf.best_s < 0.0f || sah_frustum_simple(sf.x, sf.y, sf.z));
+        mminx = fminf(mminx, lminx); mmaxx = fmaxf(mmaxx, lmaxx);
+        mminy = fminf(mminy, lminy); mmaxy = fmaxf(mmaxy, lmaxy);
+        mminz = fminf(mminz, lminz); mmaxz = fmaxf(mmaxz, lmaxz);
+        mmin_a = fminf(mmin_a, lmin_a);
+    }
+    const bool sub_simple = sub_simple_acc; /* warp-uniform: every (non-empty) sub-tile's frustum has the branch-free form */
+    /* ---- macro frustum (warp-uniform) ---- */
+    SahFrustumAxis FX, FY, FZ;
+    sah_frustum_axis_setup(FX, cam.px, mminx, mmaxx, pad, geo);
+    sah_frustum_axis_setup(FY, cam.py, mminy, mmaxy, pad, geo);
+    sah_frustum_axis_setup(FZ, cam.pz, mminz, mmaxz, pad, geo);
+    const float min_len = sqrtf(mmin_a);
+    const float cull_abs = (min_len > 0.0f) ? (2.0f * sc.r_max) / min_len : INFINITY;
+    float pkt_best_s = INFINITY;
+    const bool simple = sah_frustum_simple(FX, FY, FZ);
+
+    int top = 1;
+    if (lane == 0) stack[0] = 0;
+    __syncwarp();
+    while (top > 0) {
+        int npop = top < 8 ? top : 8;
+        if (top > dfs_from) npop = 1;
+        const int j = lane >> 2, c = lane & 3;
+        const bool active = j < npop;
+        int32_t nd = active ? stack[top - 1 - j] : 0;
+        __syncwarp();
+        top -= npop;
+        if (COUNT && lane == 0) cnt.inner += (unsigned long long)npop;
+        bool pass = false;
+        float tn = INFINITY;
+        int32_t ref = SAH_REF_NONE;
+        if (active) {
+            const float4 *rec = reinterpret_cast<const float4 *>(nodes + (size_t)nd * 32 + c * 8);
+            const float4 c0 = __ldg(rec), c1 = __ldg(rec + 1);
+            ref = __float_as_int(c1.z);
+            pass = simple ? sah_frustum_box_simple(FX, FY, FZ, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, pkt_best_s, tn)
+                          : sah_frustum_box(FX, FY, FZ, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, pkt_best_s, tn);
+            pass = pass && ref != SAH_REF_NONE;
+        }
+        const bool is_leaf = ref < 0;
+        const bool push = pass && !is_leaf;
+        const bool cand = pass && is_leaf && (uint32_t)(~ref) < (uint32_t)sc.n_spheres;
+        const uint32_t key = (__float_as_uint(tn) & 0x7ffffffcu) | (uint32_t)c;
+        int rank = 0;
+#pragma unroll
+        for (int x = 1; x < 4; x++) rank += (__shfl_xor_sync(full, key, x) < key) ? 1 : 0;
+        const int order = (7 - j) * 4 + (3 - rank);
+        unsigned ord_mask = __reduce_or_sync(full, push ? (1u << order) : 0u);
+        if (push) stack[top + __popc(ord_mask & ((1u << order) - 1u))] = ref;
+        top += __popc(ord_mask);
+        if (COUNT && (unsigned long long)top > cnt.max_stack) cnt.max_stack = (unsigned long long)top;
+        unsigned m = __ballot_sync(full, cand);
+        __syncwarp();
+        /* ---- candidates: sub-tile filter, then the reference's own tests for the rays of the sub-tiles it can touch ---- */
+        bool any_changed = false;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int32_t sidx = ~__shfl_sync(full, ref, src);
+            const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + sidx);
+            /* the candidate's own box, re-read from its node (an L1 hit, same address for every lane) */
+            const float4 *brec = reinterpret_cast<const float4 *>(nodes + (size_t)__shfl_sync(full, nd, src) * 32 + (src & 3) * 8);
+            const float4 b0 = __ldg(brec), b1 = __ldg(brec + 1);
+            const float blx = b0.x, bly = b0.y, blz = b0.z, bhx = b0.w, bhy = b1.x, bhz = b1.y;
+            bool sub_pass = false;
+            if (lane < S) {
+                const PktSubFrustum &sf = s_sub[warp][lane];
+                float tq;
+                sub_pass = sub_simple ? sah_frustum_box_simple(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq)
+                                      : sah_frustum_box(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq);
+            }
+            unsigned qmask = __ballot_sync(full, sub_pass) & ((1u << S) - 1u);
+            while (qmask) {
+                const int q = __ffs(qmask) - 1;
+                qmask &= qmask - 1;
+                /* the reference's sphere test and, for a would-be winner, its own leaf-box test, ray by ray (the box is
+                 * already here for the filter, so there is no reason to batch the box tests as K2p does) */
+                bool changed = false;
+                const float *rq = &s_ray[warp][q][0][0][lane];   /* ray k: rq[k*96], rq[k*96+32], rq[k*96+64] */
+                float *btq = &s_bt[warp][q][0][lane];            /* ray k: btq[k*32] */
+                int32_t *bpq = &s_bp[warp][q][0][lane];
+                unsigned vq = (valid >> (q * 4)) & 15u;
+#pragma unroll 1
+                for (; vq; vq &= vq - 1u, rq += 0) {
+                    const int k = __ffs(vq) - 1;
+                    SahRay r;
+                    r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
+                    r.dx = rq[k * 96]; r.dy = rq[k * 96 + 32]; r.dz = rq[k * 96 + 64];
+                    r.a = F_ADD(F_ADD(F_MUL(r.dx, r.dx), F_MUL(r.dy, r.dy)), F_MUL(r.dz, r.dz));
+                    if (COUNT) cnt.spheres++;
+                    float t;
+                    if (sah_sphere_t(r, s.x, s.y, s.z, s.w, t)) {
+                        const float bt = btq[k * 32];
+                        const int32_t bp = bpq[k * 32];
+                        if (bp < 0 || t < bt || (t == bt && sidx > bp)) {
+                            if (COUNT) cnt.exact++;
+                            if (sah_box_exact_fast(r, blx, bly, blz, bhx, bhy, bhz)) {
+                                btq[k * 32] = t;
+                                bpq[k * 32] = sidx;
+                                changed = true;
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(full, changed)) {
+                    float w = 0.0f; /* worst (largest) cull bound over this lane's valid rays of sub-tile q */
+#pragma unroll
+                    for (int k = 0; k < PKT_K; k++)
+                        if (valid & (1u << (q * 4 + k)))
+                            w = fmaxf(w, s_bp[warp][q][k][lane] >= 0 ? F_FMA(s_bt[warp][q][k][lane], SAH_REL_CULL, cull_abs) : INFINITY);
+                    w = warp_max_nonneg(w);
+                    if (lane == 0) s_sub[warp][q].best_s = w;
+                    any_changed = true;
+                }
+            }
+            __syncwarp(); /* the next candidate's filter reads the bounds just written */
+        }
+        if (any_changed) { /* warp-uniform */
+            float w = 0.0f;
+#pragma unroll
+            for (int q = 0; q < S; q++) w = fmaxf(w, s_sub[warp][q].best_s);
+            pkt_best_s = w;
+        }
+    }
+    /* ---- results: the warp's own 32-pixel rows ---- */
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < MROWS; r++) {
+        const int py = y0 + ty * MROWS + r, bx = tx * 32 + lane;
+        if (py >= y1 || bx >= width) continue;
+        const int q = (r >> 3) * 2 + (lane >> 4);
+        const int k = (((r & 7) >> 2) << 1) | ((lane >> 3) & 1);
+        const int l2 = ((r & 3) << 3) | (lane & 7);
+        const int32_t bp = s_bp[warp][q][k][l2];
+        const float bt = s_bt[warp][q][k][l2];
+        const size_t pix = (size_t)(py - y0) * (size_t)width + (size_t)bx;
+        if (ids_mode == SAH_IDS_PRIM) reinterpret_cast<int32_t *>(ids)[pix] = bp;
+        else if (ids_mode == SAH_IDS_TPRIM) ids[pix] = make_float2(bp >= 0 ? bt : 0.0f, __int_as_float(bp));
+        if (RECORDS) {
+            SahHit h;
+            if (bp >= 0) {
+                SahRay ray;
+                ray.ox = cam.px; ray.oy = cam.py; ray.oz = cam.pz;
+                ray.dx = s_ray[warp][q][k][0][l2]; ray.dy = s_ray[warp][q][k][1][l2]; ray.dz = s_ray[warp][q][k][2][l2];
                 const float4 s = __ldg(reinterpret_cast<const float4 *>(spheres4) + bp);
                 sah_finish_hit(ray, bt, bp, s.x, s.y, s.z, h);
             } else {
@@ -1145,6 +1398,11 @@ extern "C" void gpu_bvh_free(gpu_bvh *b)
     if (b->d_special) cudaFree(b->d_special);
     if (b->d_wide_full) cudaFree(b->d_wide_full);
     if (b->d_render) cudaFree(b->d_render);
+    for (int i = 0; i < SAHBVH_TUNE_SLOTS; i++)
+        for (int k = 0; k < 2; k++)
+            for (int sidx = 0; sidx < 2; sidx++)
+                for (int e = 0; e < 2; e++)
+                    if (b->tune[i].ev[k][sidx][e]) cudaEventDestroy(b->tune[i].ev[k][sidx][e]);
     free(b);
 }
 
@@ -1324,6 +1582,72 @@ void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c)
     c->fh = (float)height;
 }
 
+/* SAHBVH_PRIMARY_AUTO.  K2p (16 x 8 tiles) and K2m (32 x 8 macro tiles with a sub-tile filter) return identical
+ * records; which is faster depends on the scene and the frame (K2m: 5-17 % faster on the 5 K - 1 M sphere 4K frames, K2p
+ * 25 % faster on the 10 M one and on small frames).  Per handle and frame shape the first launches
+ * alternate between the two with an event pair around each; once two samples of each have completed the faster one
+ * (minimum of its samples) is used from then on.  Nothing synchronises: the events are only queried.  Instrumented
+ * (counting) launches use the decision when there is one and K2p otherwise. */
+static PrimaryTune *primary_tune_find(gpu_bvh *b, int width, int rows, bool create)
+{
+    for (int i = 0; i < b->n_tune; i++)
+        if (b->tune[i].width == width && b->tune[i].rows == rows) return &b->tune[i];
+    if (!create) return nullptr;
+    PrimaryTune *t = &b->tune[b->n_tune < SAHBVH_TUNE_SLOTS ? b->n_tune++ : (b->tune_evict++ % SAHBVH_TUNE_SLOTS)];
+    t->width = width;
+    t->rows = rows;
+    t->decided = -1;
+    t->launches = 0;
+    return t;
+}
+
+static int primary_tune_pick(gpu_bvh *b, int width, int rows, bool count, cudaEvent_t *start, cudaEvent_t *stop)
+{
+    PrimaryTune *t = primary_tune_find(b, width, rows, !count);
+    if (!t) return SAHBVH_PRIMARY_PACKET;
+    if (t->decided >= 0 || count) return t->decided >= 0 ? t->decided : SAHBVH_PRIMARY_PACKET;
+    const int n = t->launches++;
+    if (n >= 6) {
+        /* samples 1 and 2 of each kernel (launches 2..5; 0 and 1 were warm-up): decide once all of them have completed */
+        float ms[2] = {1e30f, 1e30f};
+        bool ready = true;
+        for (int k = 0; k < 2 && ready; k++)
+            for (int sidx = 0; sidx < 2 && ready; sidx++) {
+                float v = 0.0f;
+                const cudaError_t e = cudaEventElapsedTime(&v, t->ev[k][sidx][0], t->ev[k][sidx][1]);
+                if (e == cudaSuccess) ms[k] = v < ms[k] ? v : ms[k];
+                else { (void)cudaGetLastError(); ready = false; }
+            }
+        if (ready) t->decided = ms[1] < ms[0] ? SAHBVH_PRIMARY_MACRO : SAHBVH_PRIMARY_PACKET;
+        else if (n >= 64) t->decided = SAHBVH_PRIMARY_PACKET; /* events never completed (capturing stream?): stop trying */
+        return t->decided >= 0 ? t->decided : SAHBVH_PRIMARY_PACKET;
+    }
+    const int k = n & 1;
+    if (n >= 2) {
+        const int sidx = (n >> 1) - 1;
+        for (int e = 0; e < 2; e++)
+            if (!t->ev[k][sidx][e] && cudaEventCreate(&t->ev[k][sidx][e]) != cudaSuccess) {
+                (void)cudaGetLastError();
+                t->decided = SAHBVH_PRIMARY_PACKET; /* no events, no tuning */
+                return t->decided;
+            }
+        *start = t->ev[k][sidx][0];
+        *stop = t->ev[k][sidx][1];
+    }
+    return k ? SAHBVH_PRIMARY_MACRO : SAHBVH_PRIMARY_PACKET;
+}
+
+/* 0 per-ray, 1 K2p, 2 K2m: the kernel gpu_trace_primary* uses for this handle and frame shape right now; -1 while
+ * SAHBVH_PRIMARY_AUTO is still sampling */
+extern "C" int gpu_primary_kernel_in_use(const gpu_bvh *b, int width, int rows)
+{
+    if (!b) return SAHBVH_E_ARG;
+    const int mode = g_primary_mode.load();
+    if (mode != SAHBVH_PRIMARY_AUTO) return mode;
+    const PrimaryTune *t = primary_tune_find(const_cast<gpu_bvh *>(b), width, rows, false);
+    return t ? t->decided : -1;
+}
+
 int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, int y0, int y1, void *d_out,
                           cudaStream_t st, bool count, void *d_ids, int ids_mode)
 {
@@ -1338,7 +1662,13 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
     gpu_hit *out = (gpu_hit *)d_out;
     float2 *ids = (float2 *)d_ids;
     const SahScene sc = sahbvh_make_scene(b->info);
-    if (g_primary_mode.load() == SAHBVH_PRIMARY_PACKET) {
+    /* which kernel: fixed by the mode, or -- SAHBVH_PRIMARY_AUTO -- the faster of the two packet kernels for this
+     * handle and frame shape, found by timing the first launches (primary_tune_pick) */
+    int kernel = g_primary_mode.load();
+    cudaEvent_t tune_start = nullptr, tune_stop = nullptr;
+    if (kernel == SAHBVH_PRIMARY_AUTO) kernel = primary_tune_pick(b, width, y1 - y0, count, &tune_start, &tune_stop);
+    if (tune_start) cudaEventRecord(tune_start, st);
+    if (kernel == SAHBVH_PRIMARY_PACKET || kernel == SAHBVH_PRIMARY_MACRO) {
         /* one CTA per 32 x 16 pixel group (2 x 2 tiles of 16 x 8) */
         const long long groups = (long long)((width + 31) / 32) * ((y1 - y0 + PKT_GROUP_ROWS * PKT_TILE_H - 1) / (PKT_GROUP_ROWS * PKT_TILE_H));
         if (groups >= (1ll << 31) - 1) {
@@ -1348,7 +1678,22 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
         const unsigned grid = (unsigned)groups;
         const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth);
         L2Window win(b, st, b->d_wide_full, (size_t)b->n_wide * 128);
-        if (count)
+        if (kernel == SAHBVH_PRIMARY_MACRO) {
+            /* macro tiles: one warp per 32 x 8 pixels, four of them per block in row-major order */
+            const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth, PKT_MACRO_STACK);
+            const long long mtiles = (long long)((width + 31) / 32) * ((y1 - y0 + 7) / 8);
+            const int mw = PKT_MACRO_WARPS(1);
+            const unsigned mgrid = (unsigned)((mtiles + mw - 1) / mw);
+            if (count)
+                k_trace_primary_macro<true, true, 1><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                                                                               out, ids, ids_mode, dfs_from, b->d_counters);
+            else if (out)
+                k_trace_primary_macro<false, true, 1><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                                                                                out, ids, ids_mode, dfs_from, nullptr);
+            else
+                k_trace_primary_macro<false, false, 1><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                                                                                 nullptr, ids, ids_mode, dfs_from, nullptr);
+        } else if (count)
             k_trace_primary_packet<true, true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                out, ids, ids_mode, dfs_from, b->d_counters);
         else if (out)
@@ -1368,6 +1713,7 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
             k_trace_primary<false><<<grid, PRIMARY_THREADS, 0, st>>>(b->d_nodes, b->d_spheres4, sc, c, width, y0, y1,
                                                                     out, ids, ids_mode, nullptr);
     }
+    if (tune_stop) cudaEventRecord(tune_stop, st);
     g_launches++;
     CU_TRY(cudaGetLastError());
     return SAHBVH_OK;

@@ -190,12 +190,21 @@ int sahbvh_host_alloc(size_t bytes, void **ptr);
 int sahbvh_host_free(void *ptr);
 int sahbvh_host_pin(void *ptr, size_t bytes);
 int sahbvh_host_unpin(void *ptr);
-/* Which kernel gpu_trace_primary* launches (process-wide; both give identical hit records):
- *   SAHBVH_PRIMARY_PACKET  (default) one warp per 16x8 pixel tile, interior culling once per tile
+/* Which kernel gpu_trace_primary* launches (process-wide; all give identical hit records):
+ *   SAHBVH_PRIMARY_PACKET  one warp per 16x8 pixel tile, interior culling once per tile
  *   SAHBVH_PRIMARY_PER_RAY one thread per pixel, per-ray stack traversal (the ray-buffer kernel's core) */
 #define SAHBVH_PRIMARY_PER_RAY 0
 #define SAHBVH_PRIMARY_PACKET 1
+/*   SAHBVH_PRIMARY_MACRO   one warp per 32x8 pixel macro tile: interior culling once per 256 rays, a candidate leaf is
+ *                          first tested against the two 16x8 sub-tile frusta and only their rays run the exact tests
+ *   SAHBVH_PRIMARY_AUTO    (default) PACKET or MACRO, whichever the first launches on this handle and frame shape
+ *                          measure as faster (event pairs around the launches, queried later; nothing synchronises) */
+#define SAHBVH_PRIMARY_MACRO 2
+#define SAHBVH_PRIMARY_AUTO 3
 int sahbvh_set_primary_mode(int mode);
+/* the kernel in use for this handle and frame shape (rows = y1 - y0): one of the modes above, or -1 while
+ * SAHBVH_PRIMARY_AUTO is still sampling (its first six launches of that shape) */
+int gpu_primary_kernel_in_use(const gpu_bvh *bvh, int width, int rows);
 /* Which kernel gpu_trace_closest_hit* launches (identical hit records):
  *   SAHBVH_RAYS_WIDE     (default) persistent warps over the 4-wide, 8-bit quantised tree (64-byte
  *                        nodes, two binary levels per fetch), shared-memory stack, batched ray refill

@@ -112,13 +112,13 @@ def test_fuzz_gpu(pkg, oracle, seed, n):
             for mode in (gpu.RAYS_WIDE, gpu.RAYS_COOP, gpu.RAYS_ONE_SHOT):
                 gpu.set_ray_mode(mode)
                 assert_hits_equal(bvh.trace_closest_hit(rays), want, f"fuzz seed {seed} n {n} ray mode {mode} build {build_mode}")
-            for pmode in (gpu.PRIMARY_PACKET, gpu.PRIMARY_PER_RAY):
+            for pmode in (gpu.PRIMARY_PACKET, gpu.PRIMARY_MACRO, gpu.PRIMARY_PER_RAY):
                 gpu.set_primary_mode(pmode)
                 assert_hits_equal(bvh.trace_primary(cam, 320, 200), prim_want, f"fuzz seed {seed} n {n} primary mode {pmode}")
             # compact outputs: the ids are the records' ids, {t, prim} the records' t, and the records derived from
             # the ids on demand are the reference's records
             gpu.set_ray_mode(gpu.RAYS_WIDE)
-            gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+            gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
             assert same(bvh.trace_closest_hit_prims(rays), want["prim"])
             ids = bvh.trace_primary_prims(cam, 320, 200)
             assert same(ids, prim_want["prim"])
@@ -131,4 +131,4 @@ def test_fuzz_gpu(pkg, oracle, seed, n):
         set_keep_binary(gpu, keep_before)
         gpu.set_build_mode(gpu.BUILD_DEVICE)
         gpu.set_ray_mode(gpu.RAYS_WIDE)
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)

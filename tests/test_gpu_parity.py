@@ -429,6 +429,9 @@ def test_packet_and_per_ray_primary_kernels_agree(gpu, oracle, scene100k):
                                   (cam2, (640, 360, 0, 360)), (cam, (17, 9, 0, 9)), (cam2, (3840, 2160, 1000, 1100))):
             gpu.set_primary_mode(gpu.PRIMARY_PACKET)
             a = bvh.trace_primary(c, w, h, y0, y1)
+            gpu.set_primary_mode(gpu.PRIMARY_MACRO)
+            am = bvh.trace_primary(c, w, h, y0, y1)
+            assert_hits_equal(am, a, f"macro-tile vs packet {w}x{h} rows [{y0},{y1})")
             gpu.set_primary_mode(gpu.PRIMARY_PER_RAY)
             b = bvh.trace_primary(c, w, h, y0, y1)
             assert_hits_equal(a, b, f"packet vs per-ray {w}x{h} rows [{y0},{y1})")
@@ -436,7 +439,7 @@ def test_packet_and_per_ray_primary_kernels_agree(gpu, oracle, scene100k):
                 want, _ = oracle.trace_bvh(nodes, s, 100000, oracle.primary_rays(c, w, h, y0, y1))
                 assert_hits_equal(a, want, f"packet vs oracle {w}x{h}")
     finally:
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
 
 
 def test_ray_buffer_kernels_agree(gpu, oracle, scene100k):
@@ -721,6 +724,8 @@ def test_10m_config5_scale(gpu):
         rows = (2000, 2032)
         gpu.set_primary_mode(gpu.PRIMARY_PACKET)
         a = bd.trace_primary(cam, W, H, *rows)
+        gpu.set_primary_mode(gpu.PRIMARY_MACRO)
+        assert_hits_equal(bd.trace_primary(cam, W, H, *rows), a, "10M: macro-tile vs packet primary")
         gpu.set_primary_mode(gpu.PRIMARY_PER_RAY)
         b = bd.trace_primary(cam, W, H, *rows)
         assert_hits_equal(a, b, "10M: packet vs per-ray primary")
@@ -749,7 +754,7 @@ def test_10m_config5_scale(gpu):
         bd.close()
     finally:
         gpu.set_build_mode(gpu.BUILD_DEVICE)
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
         gpu.set_ray_mode(gpu.RAYS_WIDE)
 
 

@@ -114,12 +114,12 @@ def test_default_handle_has_no_binary_tree(gpu, scene100k):
         gpu.set_primary_mode(gpu.PRIMARY_PER_RAY)
         with pytest.raises(gpu.SahBvhError, match="binary tree"):
             bvh.trace_primary(cam, 64, 32)
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
         gpu.set_ray_mode(gpu.RAYS_COOP)
         with pytest.raises(gpu.SahBvhError, match="binary tree"):
             bvh.trace_closest_hit(gpu.benchmark_rays(8))
     finally:
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
         gpu.set_ray_mode(gpu.RAYS_WIDE)
     assert (bvh.trace_primary(cam, 64, 32)["prim"] >= -1).all()     # the handle still works
 
@@ -171,6 +171,8 @@ def test_packet_stack_on_deep_trees_and_coarse_frames(gpu, oracle, kind):
         for W, H in ((16, 8), (64, 36), (33, 17), (320, 200)):
             gpu.set_primary_mode(gpu.PRIMARY_PACKET)
             a = bvh.trace_primary(cam, W, H)
+            gpu.set_primary_mode(gpu.PRIMARY_MACRO)
+            assert_hits_equal(bvh.trace_primary(cam, W, H), a, f"{kind} {W}x{H}: macro-tile vs packet")
             gpu.set_primary_mode(gpu.PRIMARY_PER_RAY)
             b = bvh.trace_primary(cam, W, H)
             assert_hits_equal(a, b, f"{kind} {W}x{H}: packet vs per-ray")
@@ -179,7 +181,7 @@ def test_packet_stack_on_deep_trees_and_coarse_frames(gpu, oracle, kind):
                 assert_hits_equal(a, want, f"{kind} {W}x{H}: packet vs oracle")
         bvh.close()
     finally:
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
         set_keep_binary(gpu, False)
 
 
@@ -195,16 +197,19 @@ def test_packet_stack_bound_and_forced_dfs_mode(gpu, oracle, scene100k):
     buf = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
     depth = bvh.info()["max_depth"]
     try:
-        for forced in (8, 40, 0):
-            assert gpu.lib.sahbvh_set_packet_dfs_from(C.c_int(forced)) == 0
-            assert_hits_equal(bvh.trace_primary(cam, W, H), want, f"dfs_from={forced}")
-            st = bvh.trace_primary_stats(cam, W, H, 0, H, buf.data_ptr())
-            dfs_from = forced if forced else 512 - 32 - 3 * (depth + 2)
-            assert 0 < st["max_stack"] <= dfs_from + 24 + 3 * depth, (forced, st)
-            if forced == 8:
-                assert st["max_stack"] > 8                # the frame really ran in single-pop mode above the threshold
+        for mode, stack_entries in ((gpu.PRIMARY_PACKET, 512), (gpu.PRIMARY_MACRO, 256)):     # PKT_STACK / PKT_MACRO_STACK
+            gpu.set_primary_mode(mode)
+            for forced in (8, 40, 0):
+                assert gpu.lib.sahbvh_set_packet_dfs_from(C.c_int(forced)) == 0
+                assert_hits_equal(bvh.trace_primary(cam, W, H), want, f"mode {mode} dfs_from={forced}")
+                st = bvh.trace_primary_stats(cam, W, H, 0, H, buf.data_ptr())
+                dfs_from = forced if forced else stack_entries - 32 - 3 * (depth + 2)
+                assert 0 < st["max_stack"] <= dfs_from + 24 + 3 * depth, (mode, forced, st)
+                if forced == 8:
+                    assert st["max_stack"] > 8            # the frame really ran in single-pop mode above the threshold
     finally:
         gpu.lib.sahbvh_set_packet_dfs_from(C.c_int(0))
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
 
 
 def test_scalar_cache_survives_foreign_free_and_address_reuse(gpu, oracle):
@@ -375,6 +380,34 @@ def test_random_cameras_and_odd_frames(gpu, oracle, scene100k):
             assert same(bvh.trace_primary_prims(cam, W, H), want["prim"])
 
 
+def test_primary_auto_mode_samples_then_settles(gpu, oracle, scene100k):
+    """SAHBVH_PRIMARY_AUTO: the first launches of a frame shape alternate between the two packet kernels (identical
+    records whichever runs), then the handle settles on one of them for that shape; other shapes are tuned separately
+    and counting launches never disturb the sampling."""
+    bvh0, s, nodes = scene100k
+    cam = gpu.default_camera()
+    W, H = 640, 360
+    want, _ = oracle.trace_bvh(nodes, s, 100000, oracle.primary_rays(cam, W, H))
+    bvh = gpu.GpuBvh.build(s.copy(), 100000, 0, 100000, 0)      # a fresh handle: no tuning history
+    try:
+        gpu.set_primary_mode(gpu.PRIMARY_AUTO)
+        assert bvh.primary_kernel_in_use(W, H) == -1
+        seen = set()
+        for k in range(12):
+            assert_hits_equal(bvh.trace_primary(cam, W, H), want, f"auto mode, launch {k}")
+            seen.add(bvh.primary_kernel_in_use(W, H))
+        assert bvh.primary_kernel_in_use(W, H) in (gpu.PRIMARY_PACKET, gpu.PRIMARY_MACRO)   # settled (host calls synchronise)
+        assert -1 in seen                                                                   # ... after a sampling phase
+        assert bvh.primary_kernel_in_use(W, 48) == -1                                       # another shape: its own entry
+        assert same(bvh.trace_primary_prims(cam, W, H, 100, 148), want["prim"][100 * W:148 * W])
+        for mode in (gpu.PRIMARY_PACKET, gpu.PRIMARY_MACRO, gpu.PRIMARY_PER_RAY):
+            gpu.set_primary_mode(mode)
+            assert bvh.primary_kernel_in_use(W, H) == mode
+    finally:
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
+        bvh.close()
+
+
 def test_l2_persisting_window_option_changes_nothing_but_residency(gpu, oracle, scene100k):
     """sahbvh_set_l2_persist_bytes: trace launches run with an access-policy window over the top of the breadth-first
     node array; records stay bit-identical, and switching it off again restores the default launches."""
@@ -431,9 +464,12 @@ def test_1m_4k_full_frame_kernels_agree_and_oracle_sample(gpu, oracle):
         a = bvh.trace_primary(cam, W, H)
         prims = bvh.trace_primary_prims(cam, W, H)
         assert same(prims, a["prim"])
+        gpu.set_primary_mode(gpu.PRIMARY_MACRO)
+        assert_hits_equal(bvh.trace_primary(cam, W, H), a, "1M 4K: macro-tile vs packet, full frame")
+        assert same(bvh.trace_primary_prims(cam, W, H), prims)
         gpu.set_primary_mode(gpu.PRIMARY_PER_RAY)
         b = bvh.trace_primary(cam, W, H)
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
         assert_hits_equal(a, b, "1M 4K: packet vs per-ray, full frame")
         rays = gpu.generate_primary_rays(cam, W, H)
         assert same(rays, oracle.primary_rays(cam, W, H))
@@ -453,7 +489,7 @@ def test_1m_4k_full_frame_kernels_agree_and_oracle_sample(gpu, oracle):
         assert same(bvh.trace_closest_hit_prims(br), bh["prim"])
         bvh.close()
     finally:
-        gpu.set_primary_mode(gpu.PRIMARY_PACKET)
+        gpu.set_primary_mode(gpu.PRIMARY_DEFAULT)
         set_keep_binary(gpu, False)
 
 

@@ -22,7 +22,7 @@ buf = torch.empty((W * H, 8), dtype=torch.float32, device="cuda")
 flush = torch.empty(160 << 20, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
 ref = None
-for mode in (pkg.PRIMARY_PACKET, pkg.PRIMARY_PER_RAY):
+for mode in (pkg.PRIMARY_PACKET, pkg.PRIMARY_MACRO, pkg.PRIMARY_PER_RAY):
     pkg.set_primary_mode(mode)
     for _ in range(3):
         bvh.trace_primary_dev(cam, W, H, 0, H, buf.data_ptr(), stream)
@@ -42,7 +42,7 @@ for mode in (pkg.PRIMARY_PACKET, pkg.PRIMARY_PER_RAY):
         ref = h
     print(f"mode {mode}: {np.mean(ms):.4f} ms (min {np.min(ms):.4f})  {W * H / np.mean(ms) / 1e6:.2f} Grays/s  same_as_first {same}", flush=True)
 
-pkg.set_primary_mode(pkg.PRIMARY_PACKET)
+pkg.set_primary_mode(int(os.environ.get('PRIMARY_MODE', pkg.PRIMARY_MACRO)))
 ids = torch.empty((W * H,), dtype=torch.int32, device="cuda")
 for _ in range(3):
     bvh.trace_primary_dev_prims(cam, W, H, 0, H, 0, ids.data_ptr(), stream)
