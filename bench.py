@@ -394,7 +394,7 @@ class FrameGather:
         self.cons = torch.cuda.Stream()
         self.cons_done = [None, None]
         self.own_done = None
-        self.root_share = 1.0      # calibrate() shortens rank 0's band by the consumer's cost
+        self.rows_table = {}       # calibrate(): measured, load-balanced bands per frame height
         self.calibration = None
         if self.ok:
             self.flags = self.ptrs[2]
@@ -438,34 +438,54 @@ class FrameGather:
         ev.record(self.cons)
         self.cons_done[k & 1] = ev
 
-    def calibrate(self, bvh, cam, W, H, d_records, reps=5):
-        """Load balance: rank 0 traces its band AND consumes every frame, so its band is shortened until all ranks
-        finish a frame together.  t = event time of an equal band (mean over ranks), c = event time of the consumer's
-        pass over the whole frame on rank 0; root_share = 1 - (c/t)(N-1)/N (sahbvh_shard_rows_weighted)."""
+    def calibrate(self, bvh, cam, W, H, d_records, reps=4, rounds=2):
+        """Load balance by measurement.  Bands of equal height do not cost the same (the frame's rows see different parts
+        of the scene) and rank 0 also consumes every frame (c = event time of the consumer's pass over the whole frame).
+        Two rounds of: every rank times its current band (t_r), the times are shared, and the band heights are rescaled
+        to h_r * (T - c [r = 0]) / t_r with T = (sum t_r + c) / N, in whole 16-row blocks."""
         env, pkg, torch = self.env, self.env.pkg, self.env.torch
-        y0, y1 = pkg.shard_rows(H, env.rank, env.world)
+        world, rank = env.world, env.rank
         buf = self.ptrs[0]
-        fn = lambda: bvh.trace_primary_dev_prims(cam, W, H, y0, y1, d_records, buf + y0 * W * 4, env.stream)
-        env.fence()
-        t = time_steps(torch, fn, reps, 2, env.flush)[0] / reps
-        env.fence()
+        blocks = (H + 15) // 16
+        bounds = [blocks * r // world for r in range(world + 1)]
         c = 0.0
-        if env.rank == 0:
+        if rank == 0:
             c = time_steps(torch, lambda: pkg.count_prims_dev(buf, W * H, self.count.data_ptr(), env.stream), reps, 2, env.flush)[0] / reps
-        tc = torch.tensor([t / env.world, c], dtype=torch.float64, device="cuda")
-        env.dist.all_reduce(tc, op=env.dist.ReduceOp.SUM)
-        t_mean, c = float(tc[0].item()), float(tc[1].item())
-        share = 1.0 - (c / t_mean) * (env.world - 1) / env.world if t_mean > 0 else 1.0
-        self.root_share = min(1.0, max(0.5, share))
-        self.calibration = {"equal_band_ms": t_mean, "consumer_ms": c, "root_share": self.root_share,
-                            "rows": [pkg.shard_rows_weighted(H, r, env.world, self.root_share) for r in range(env.world)]}
+        history = []
+        for _ in range(rounds):
+            y0, y1 = bounds[rank] * 16, min(bounds[rank + 1] * 16, H)
+            settle_primary(torch, bvh, cam, W, H, y0, y1, d_records, env.stream)
+            fn = lambda: bvh.trace_primary_dev_prims(cam, W, H, y0, y1, d_records, buf + y0 * W * 4, env.stream)
+            env.fence()
+            t = time_steps(torch, fn, reps, 2, env.flush)[0] / reps
+            env.fence()
+            ts = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+            env.dist.all_gather(ts, torch.tensor([t, c], dtype=torch.float64, device="cuda"))
+            t_all = [float(v[0].item()) for v in ts]
+            c_all = float(ts[0][1].item())
+            history.append({"rows": [(bounds[r] * 16, min(bounds[r + 1] * 16, H)) for r in range(world)], "band_ms": t_all})
+            target = (sum(t_all) + c_all) / world
+            want = [(bounds[r + 1] - bounds[r]) * max(target - (c_all if r == 0 else 0.0), 0.25 * target) / max(t_all[r], 1e-6) for r in range(world)]
+            scale = blocks / sum(want)
+            acc, nb = 0.0, [0]
+            for r in range(world):
+                acc += want[r] * scale
+                nb.append(max(nb[-1] + 1, min(blocks - (world - 1 - r), int(round(acc)))))
+            nb[-1] = blocks
+            bounds = nb
+        self.rows_table = {H: [(bounds[r] * 16, min(bounds[r + 1] * 16, H)) for r in range(world)]}
+        self.calibration = {"consumer_ms": c_all, "rounds": history, "rows": self.rows_table[H]}
+        y0, y1 = self.rows_table[H][rank]
+        settle_primary(torch, bvh, cam, W, H, y0, y1, d_records, env.stream)
         self.count.zero_()
         env.fence()
         return self.calibration
 
     def band(self, H, balanced, rank=None):
         rank = self.env.rank if rank is None else rank
-        return self.env.pkg.shard_rows_weighted(H, rank, self.env.world, self.root_share if balanced else 1.0)
+        if balanced and H in self.rows_table:
+            return self.rows_table[H][rank]
+        return self.env.pkg.shard_rows(H, rank, self.env.world)
 
     def frames(self, bvh, cam, W, H, k_steps, d_records, flush=True, timeout_ms=10000, balanced=False):
         """K frames of rows sharded over the ranks (balanced: with the calibrated shorter band for rank 0); returns
@@ -588,8 +608,6 @@ def run_b200(args):
     kernel_id = settle_primary(torch, bvh, cam, W, H, y0, y1, hits_local.data_ptr(), stream)
     if gather is not None:
         gather.calibrate(bvh, cam, W, H, hits_local.data_ptr())
-        by0, by1 = gather.band(H, True)
-        settle_primary(torch, bvh, cam, W, H, by0, by1, hits_local.data_ptr(), stream)
     run_steps(args.warmup)
     env.fence()
     if gather is not None:
