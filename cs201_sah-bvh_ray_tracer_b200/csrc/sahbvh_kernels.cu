@@ -758,6 +758,13 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
 #ifndef PKT_MACRO_STACK
 #define PKT_MACRO_STACK 256
 #endif
+#ifndef PKT_PREFETCH
+#define PKT_PREFETCH 0 /* L1 prefetch of the next step's nodes before a candidate phase: measured 0.3785 ms against 0.3729 ms without */
+#endif
+#ifndef PKT_RAY_UNROLL
+#define PKT_RAY_UNROLL 1
+#endif
+static constexpr int kPktRayUnroll = PKT_RAY_UNROLL;
 static_assert(PKT_MACRO_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_MACRO_STACK too small for the deepest admissible tree");
 #define PKT_MACRO_WARPS(SUBY) (4 / (SUBY)) /* warps per block: 4 x 9 KB of per-warp state at SUBY = 1, 2 x 17 KB at SUBY = 2 */
 struct PktSubFrustum {
@@ -891,6 +898,17 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
         if (COUNT && (unsigned long long)top > cnt.max_stack) cnt.max_stack = (unsigned long long)top;
         unsigned m = __ballot_sync(full, cand);
         __syncwarp();
+#if PKT_PREFETCH
+        if (m && top > 0) {
+            /* the candidate phase below is long and does not touch the stack: start the next step's node fetches now
+             * (the entries the next iteration pops are already in place), so that its loads hit L1 */
+            const int np = top > dfs_from ? 1 : (top < 8 ? top : 8);
+            if (j < np) {
+                const float *pn = nodes + (size_t)stack[top - 1 - j] * 32 + c * 8;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pn));
+            }
+        }
+#endif
         /* ---- candidates: sub-tile filter, then the reference's own tests for the rays of the sub-tiles it can touch ---- */
         bool any_changed = false;
         while (m) {
@@ -920,7 +938,7 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
                 float *btq = &s_bt[warp][q][0][lane];            /* ray k: btq[k*32] */
                 int32_t *bpq = &s_bp[warp][q][0][lane];
                 unsigned vq = (valid >> (q * 4)) & 15u;
-#pragma unroll 1
+#pragma unroll kPktRayUnroll
                 for (; vq; vq &= vq - 1u, rq += 0) {
                     const int k = __ffs(vq) - 1;
                     SahRay r;
