@@ -1619,11 +1619,16 @@ static PrimaryTune *primary_tune_find(gpu_bvh *b, int width, int rows, bool crea
     return t;
 }
 
-static int primary_tune_pick(gpu_bvh *b, int width, int rows, bool count, cudaEvent_t *start, cudaEvent_t *stop)
+static int primary_tune_pick(gpu_bvh *b, int width, int rows, bool count, cudaStream_t st, cudaEvent_t *start, cudaEvent_t *stop)
 {
-    PrimaryTune *t = primary_tune_find(b, width, rows, !count);
+    /* a stream that is being captured into a graph cannot be sampled (the events would become graph nodes and never
+     * report a time): such launches use what is known and leave the tuner alone */
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone;
+    if (capturing) (void)cudaGetLastError();
+    PrimaryTune *t = primary_tune_find(b, width, rows, !count && !capturing);
     if (!t) return SAHBVH_PRIMARY_PACKET;
-    if (t->decided >= 0 || count) return t->decided >= 0 ? t->decided : SAHBVH_PRIMARY_PACKET;
+    if (t->decided >= 0 || count || capturing) return t->decided >= 0 ? t->decided : SAHBVH_PRIMARY_PACKET;
     const int n = t->launches++;
     if (n >= 6) {
         /* samples 1 and 2 of each kernel (launches 2..5; 0 and 1 were warm-up): decide once all of them have completed */
@@ -1684,7 +1689,7 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
      * handle and frame shape, found by timing the first launches (primary_tune_pick) */
     int kernel = g_primary_mode.load();
     cudaEvent_t tune_start = nullptr, tune_stop = nullptr;
-    if (kernel == SAHBVH_PRIMARY_AUTO) kernel = primary_tune_pick(b, width, y1 - y0, count, &tune_start, &tune_stop);
+    if (kernel == SAHBVH_PRIMARY_AUTO) kernel = primary_tune_pick(b, width, y1 - y0, count, st, &tune_start, &tune_stop);
     if (tune_start) cudaEventRecord(tune_start, st);
     if (kernel == SAHBVH_PRIMARY_PACKET || kernel == SAHBVH_PRIMARY_MACRO) {
         /* one CTA per 32 x 16 pixel group (2 x 2 tiles of 16 x 8) */

@@ -100,7 +100,7 @@ def main():
         else:
             same = bool((ref.view(np.uint32) == h.view(np.uint32)).all())
         print(f"mode {mode}: {ms:8.3f} ms  {n / ms / 1e6:7.3f} Grays/s  nodes/ray {st['inner_visits'] / n:6.1f} "
-              f"spheres/ray {st['sphere_tests'] / n:5.2f} max_stack {st['max_stack']} max_visits {st['max_visits']} same_as_first {same}", flush=True)
+              f"spheres/ray {st['sphere_tests'] / n:5.2f} max_stack {st['max_stack']} max_visits {st['max_visits']} same_as_first {same} sha {__import__('hashlib').sha256(h.tobytes()).hexdigest()[:12]}", flush=True)
         for mb in [int(v) for v in args.l2_mb.split(",") if v]:
             pkg.set_l2_persist_bytes(mb << 20)
             for _ in range(2):
