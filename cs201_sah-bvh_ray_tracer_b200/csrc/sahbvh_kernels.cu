@@ -753,7 +753,7 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
  * leave through the warp's shared-memory state without a block barrier.
  */
 #ifndef PKT_MACRO_MIN_BLOCKS
-#define PKT_MACRO_MIN_BLOCKS 8 /* 64 registers (no spills) and 24.5 KB of shared memory per 4-warp block: 32 warps per SM */
+#define PKT_MACRO_MIN_BLOCKS 8 /* x 4 warps: 64 registers and 6.1 KB of shared memory per warp = 32 warps per SM */
 #endif
 #ifndef PKT_MACRO_STACK
 #define PKT_MACRO_STACK 256
@@ -766,14 +766,19 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
 #endif
 static constexpr int kPktRayUnroll = PKT_RAY_UNROLL;
 static_assert(PKT_MACRO_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_MACRO_STACK too small for the deepest admissible tree");
-#define PKT_MACRO_WARPS(SUBY) (4 / (SUBY)) /* warps per block: 4 x 9 KB of per-warp state at SUBY = 1, 2 x 17 KB at SUBY = 2 */
+#ifndef PKT_MACRO_WARPS1
+#define PKT_MACRO_WARPS1 1 /* warps per block: a macro tile per BLOCK (32 blocks per SM).  Nothing in the kernel is shared between
+                             the warps of a block, and a block's slot is only free again when its slowest tile ends: 1 / 2 / 4
+                             warps per block measured 0.362 / 0.365 / 0.374 ms on the 1 M-sphere 4K frame */
+#endif
+#define PKT_MACRO_WARPS(SUBY) (PKT_MACRO_WARPS1 / (SUBY)) /* warps per block: 4 x 9 KB of per-warp state at SUBY = 1, 2 x 17 KB at SUBY = 2 */
 struct PktSubFrustum {
     SahFrustumAxis x, y, z;
     float best_s; /* the sub-tile's cull bound (max over its rays of best_s) */
 };
 
 template <bool COUNT, bool RECORDS, int SUBY>
-__global__ void __launch_bounds__(PKT_MACRO_WARPS(SUBY) * 32, PKT_MACRO_MIN_BLOCKS)
+__global__ void __launch_bounds__(PKT_MACRO_WARPS(SUBY) * 32, PKT_MACRO_MIN_BLOCKS * 4 / PKT_MACRO_WARPS1)
 k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                       SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
                       int ids_mode, int dfs_from, unsigned long long *counters)
@@ -1702,7 +1707,7 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
         const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth);
         L2Window win(b, st, b->d_wide_full, (size_t)b->n_wide * 128);
         if (kernel == SAHBVH_PRIMARY_MACRO) {
-            /* macro tiles: one warp per 32 x 8 pixels, four of them per block in row-major order */
+            /* macro tiles: one warp per 32 x 8 pixels, PKT_MACRO_WARPS1 of them per block in row-major order */
             const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth, PKT_MACRO_STACK);
             const long long mtiles = (long long)((width + 31) / 32) * ((y1 - y0 + 7) / 8);
             const int mw = PKT_MACRO_WARPS(1);
