@@ -771,21 +771,22 @@ static_assert(PKT_MACRO_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_MACRO
                              the warps of a block, and a block's slot is only free again when its slowest tile ends: 1 / 2 / 4
                              warps per block measured 0.362 / 0.365 / 0.374 ms on the 1 M-sphere 4K frame */
 #endif
-#define PKT_MACRO_WARPS(SUBY) (PKT_MACRO_WARPS1 / (SUBY)) /* warps per block: 4 x 9 KB of per-warp state at SUBY = 1, 2 x 17 KB at SUBY = 2 */
 struct PktSubFrustum {
     SahFrustumAxis x, y, z;
     float best_s; /* the sub-tile's cull bound (max over its rays of best_s) */
 };
 
-template <bool COUNT, bool RECORDS, int SUBY>
-__global__ void __launch_bounds__(PKT_MACRO_WARPS(SUBY) * 32, PKT_MACRO_MIN_BLOCKS * 4 / PKT_MACRO_WARPS1)
+template <bool COUNT, bool RECORDS, int S>
+__global__ void __launch_bounds__(PKT_MACRO_WARPS1 * 32, PKT_MACRO_MIN_BLOCKS * 4 / PKT_MACRO_WARPS1)
 k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                       SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
                       int ids_mode, int dfs_from, unsigned long long *counters)
 {
-    constexpr int S = 2 * SUBY;          /* sub-tiles per macro tile: 2 across, SUBY down */
-    constexpr int MW = PKT_MACRO_WARPS(SUBY);
-    constexpr int MROWS = 8 * SUBY;      /* pixel rows of a macro tile */
+    static_assert(S == 1 || S == 2 || S == 4, "sub-tiles per macro tile");
+    constexpr int SX = S >= 2 ? 2 : 1, SY = S / SX;   /* sub-tiles across / down; S = 1 is K2p's own 16 x 8 tile, one per block */
+    constexpr int MW = PKT_MACRO_WARPS1;
+    constexpr int TW = 16 * SX;          /* pixel columns of a macro tile */
+    constexpr int MROWS = 8 * SY;        /* pixel rows of a macro tile */
     __shared__ int32_t s_stack[MW][PKT_MACRO_STACK];
     __shared__ float s_ray[MW][S][PKT_K][3][32];   /* dx, dy, dz (d.d is recomputed: shared memory decides the occupancy) */
     __shared__ float s_bt[MW][S][PKT_K][32];
@@ -793,7 +794,7 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
     __shared__ PktSubFrustum s_sub[MW][S];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mtiles_x = (width + 31) >> 5, mtiles_y = (y1 - y0 + MROWS - 1) / MROWS;
+    const int mtiles_x = (width + TW - 1) / TW, mtiles_y = (y1 - y0 + MROWS - 1) / MROWS;
     SahCounters cnt = {0, 0, 0, 0};
     unsigned long long hits = 0;
     const long long mt = (long long)blockIdx.x * MW + warp;   /* macro tiles in row-major order */
@@ -802,12 +803,13 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
     int32_t *stack = s_stack[warp];
     /* ---- the lane's 4 S rays: sub-tile q = (qy, qx), ray k as in K2p:
      *      pixel (tx*32 + qx*16 + (k&1)*8 + lane%8,  y0 + ty*MROWS + qy*8 + (k>>1)*4 + lane/8) ---- */
-    const int px0 = tx * 32 + (lane & 7), py0 = y0 + ty * MROWS + (lane >> 3);
+    const int px0 = tx * TW + (lane & 7), py0 = y0 + ty * MROWS + (lane >> 3);
     unsigned valid = 0; /* bit q*4+k */
     /* the lane's rays use 4 distinct columns: one division each (main.c:362); the loops below stay ROLLED -- the
      * IEEE division / square-root sequences of one ray set-up, one sphere test and one leaf-box test are each
      * instantiated once, which keeps the kernel inside the instruction cache (ncu: no_instruction stalls) */
-    const float u0 = sah_pixel_u(cam, px0), u1 = sah_pixel_u(cam, px0 + 8), u2 = sah_pixel_u(cam, px0 + 16), u3 = sah_pixel_u(cam, px0 + 24);
+    const float u0 = sah_pixel_u(cam, px0), u1 = sah_pixel_u(cam, px0 + 8);
+    const float u2 = SX == 2 ? sah_pixel_u(cam, px0 + 16) : 0.0f, u3 = SX == 2 ? sah_pixel_u(cam, px0 + 24) : 0.0f;
     float mminx = INFINITY, mminy = INFINITY, mminz = INFINITY, mmaxx = -INFINITY, mmaxy = -INFINITY, mmaxz = -INFINITY;
     float mmin_a = INFINITY;
     float ex = fmaxf(fabsf(cam.px - sc.lo[0]), fabsf(cam.px - sc.hi[0]));
@@ -818,7 +820,7 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
     bool sub_simple_acc = true;
 #pragma unroll 1
     for (int q = 0; q < S; q++) {
-        const int qx = q & 1, qy = q >> 1;
+        const int qx = q % SX, qy = q / SX;
         float lminx = INFINITY, lminy = INFINITY, lminz = INFINITY, lmaxx = -INFINITY, lmaxy = -INFINITY, lmaxz = -INFINITY;
         float lmin_a = INFINITY;
 #pragma unroll 1
@@ -925,14 +927,17 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
             const float4 *brec = reinterpret_cast<const float4 *>(nodes + (size_t)__shfl_sync(full, nd, src) * 32 + (src & 3) * 8);
             const float4 b0 = __ldg(brec), b1 = __ldg(brec + 1);
             const float blx = b0.x, bly = b0.y, blz = b0.z, bhx = b0.w, bhy = b1.x, bhz = b1.y;
-            bool sub_pass = false;
-            if (lane < S) {
-                const PktSubFrustum &sf = s_sub[warp][lane];
-                float tq;
-                sub_pass = sub_simple ? sah_frustum_box_simple(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq)
-                                      : sah_frustum_box(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq);
+            unsigned qmask = 1u;
+            if (S > 1) { /* compile-time: a one-tile block has nothing to filter (its frustum IS the traversal's) */
+                bool sub_pass = false;
+                if (lane < S) {
+                    const PktSubFrustum &sf = s_sub[warp][lane];
+                    float tq;
+                    sub_pass = sub_simple ? sah_frustum_box_simple(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq)
+                                          : sah_frustum_box(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq);
+                }
+                qmask = __ballot_sync(full, sub_pass) & ((1u << S) - 1u);
             }
-            unsigned qmask = __ballot_sync(full, sub_pass) & ((1u << S) - 1u);
             while (qmask) {
                 const int q = __ffs(qmask) - 1;
                 qmask &= qmask - 1;
@@ -985,15 +990,17 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
             pkt_best_s = w;
         }
     }
-    /* ---- results: the warp's own 32-pixel rows ---- */
+    /* ---- results: the warp's own rows (32 pixels = one 128-byte id row per store; a 16-pixel tile stores two rows) ---- */
     __syncwarp();
+    constexpr int RPS = 32 / TW; /* rows per warp store */
 #pragma unroll 1
-    for (int r = 0; r < MROWS; r++) {
-        const int py = y0 + ty * MROWS + r, bx = tx * 32 + lane;
+    for (int r0 = 0; r0 < MROWS; r0 += RPS) {
+        const int r = r0 + (RPS == 2 ? (lane >> 4) : 0), lx = RPS == 2 ? (lane & 15) : lane;
+        const int py = y0 + ty * MROWS + r, bx = tx * TW + lx;
         if (py >= y1 || bx >= width) continue;
-        const int q = (r >> 3) * 2 + (lane >> 4);
-        const int k = (((r & 7) >> 2) << 1) | ((lane >> 3) & 1);
-        const int l2 = ((r & 3) << 3) | (lane & 7);
+        const int q = (r >> 3) * SX + (lx >> 4);
+        const int k = (((r & 7) >> 2) << 1) | ((lx >> 3) & 1);
+        const int l2 = ((r & 3) << 3) | (lx & 7);
         const int32_t bp = s_bp[warp][q][k][l2];
         const float bt = s_bt[warp][q][k][l2];
         const size_t pix = (size_t)(py - y0) * (size_t)width + (size_t)bx;
@@ -1707,19 +1714,21 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
         const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth);
         L2Window win(b, st, b->d_wide_full, (size_t)b->n_wide * 128);
         if (kernel == SAHBVH_PRIMARY_MACRO) {
-            /* macro tiles: one warp per 32 x 8 pixels, PKT_MACRO_WARPS1 of them per block in row-major order */
+            /* macro tiles: one warp per 32 x 8 pixels (S = 2 sub-tiles), PKT_MACRO_WARPS1 of them per block in row-major order.
+             * The template also instantiates for S = 1 (one 16 x 8 tile per block: 0.418 ms on the headline frame against
+             * K2p's 0.391) and S = 4 (32 x 16: 0.408 ms, shared memory limits it to 18 warps per SM); only S = 2 ships. */
             const int dfs_from = sahbvh_packet_dfs_from(b->info.max_depth, PKT_MACRO_STACK);
             const long long mtiles = (long long)((width + 31) / 32) * ((y1 - y0 + 7) / 8);
-            const int mw = PKT_MACRO_WARPS(1);
+            const int mw = PKT_MACRO_WARPS1;
             const unsigned mgrid = (unsigned)((mtiles + mw - 1) / mw);
             if (count)
-                k_trace_primary_macro<true, true, 1><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                k_trace_primary_macro<true, true, 2><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                out, ids, ids_mode, dfs_from, b->d_counters);
             else if (out)
-                k_trace_primary_macro<false, true, 1><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                k_trace_primary_macro<false, true, 2><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                 out, ids, ids_mode, dfs_from, nullptr);
             else
-                k_trace_primary_macro<false, false, 1><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                k_trace_primary_macro<false, false, 2><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                  nullptr, ids, ids_mode, dfs_from, nullptr);
         } else if (count)
             k_trace_primary_packet<true, true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
