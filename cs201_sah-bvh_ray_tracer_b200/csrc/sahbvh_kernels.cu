@@ -1613,8 +1613,8 @@ void sahbvh_make_camera(const Camera *cam, int width, int height, SahCamera *c)
 }
 
 /* SAHBVH_PRIMARY_AUTO.  K2p (16 x 8 tiles) and K2m (32 x 8 macro tiles with a sub-tile filter) return identical
- * records; which is faster depends on the scene and the frame (K2m: 5-17 % faster on the 5 K - 1 M sphere 4K frames, K2p
- * 25 % faster on the 10 M one and on small frames).  Per handle and frame shape the first launches
+ * records; which is faster depends on the scene and the frame (K2m: 7-19 % faster on the 5 K - 1 M sphere 4K frames, K2p
+ * 12 % faster on the 10 M one).  Per handle and frame shape the first launches
  * alternate between the two with an event pair around each; once two samples of each have completed the faster one
  * (minimum of its samples) is used from then on.  Nothing synchronises: the events are only queried.  Instrumented
  * (counting) launches use the decision when there is one and K2p otherwise. */
