@@ -35,7 +35,15 @@ static_assert(SAH_STACK_MAX == SAHBVH_STACK_MAX, "stack depth");
 #define PRIMARY_THREADS 256 /* 32 x 8 pixels per CTA, one 8x4 tile per warp */
 
 std::atomic<unsigned long long> g_launches{0};
-static std::atomic<int> g_primary_mode{SAHBVH_PRIMARY_AUTO};
+/* the process-wide default can be pinned from the environment (SAHBVH_PRIMARY_MODE=0..3): profiler runs use it, because
+ * under ncu every launch is serialised and replayed and the AUTO tuner's event times mean nothing */
+static int initial_primary_mode()
+{
+    const char *e = getenv("SAHBVH_PRIMARY_MODE");
+    const int v = e ? atoi(e) : SAHBVH_PRIMARY_AUTO;
+    return (e && v >= SAHBVH_PRIMARY_PER_RAY && v <= SAHBVH_PRIMARY_AUTO) ? v : SAHBVH_PRIMARY_AUTO;
+}
+static std::atomic<int> g_primary_mode{initial_primary_mode()};
 static std::atomic<int> g_ray_mode{SAHBVH_RAYS_WIDE};
 static std::atomic<int> g_build_mode{SAHBVH_BUILD_DEVICE};
 static std::atomic<int> g_keep_binary{0};

@@ -201,7 +201,7 @@ int sahbvh_host_unpin(void *ptr);
  *                          measure as faster (event pairs around the launches, queried later; nothing synchronises) */
 #define SAHBVH_PRIMARY_MACRO 2
 #define SAHBVH_PRIMARY_AUTO 3
-int sahbvh_set_primary_mode(int mode);
+int sahbvh_set_primary_mode(int mode);   /* the environment variable SAHBVH_PRIMARY_MODE=0..3 sets the initial mode */
 /* the kernel in use for this handle and frame shape (rows = y1 - y0): one of the modes above, or -1 while
  * SAHBVH_PRIMARY_AUTO is still sampling (its first six launches of that shape) */
 int gpu_primary_kernel_in_use(const gpu_bvh *bvh, int width, int rows);
