@@ -92,6 +92,9 @@ def test_interior_tests_never_reject_what_the_reference_accepts(oracle, em, kind
     assert r["accepted"] > 100 and r["bad_binary"] == 0 and r["bad_wide"] == 0, r
     f = em.check_frustum(h, cam, 320, 180, tile_step=1 if n <= 3000 else 5, node_step=1 if n <= 3000 else 3)
     assert f["accepted"] > 100 and f["bad"] == 0 and f["bad_simple"] == 0, f
+    # the macro-tile kernel culls with the frustum of a 32 x 8 pixel tile (and filters leaves with its 16 x 8 halves, above)
+    f = em.check_frustum(h, cam, 320, 180, tile_w=32, tile_h=8, tile_step=1 if n <= 3000 else 3, node_step=1 if n <= 3000 else 3)
+    assert f["accepted"] > 100 and f["bad"] == 0 and f["bad_simple"] == 0, f
     em.free(h)
 
 
@@ -109,6 +112,8 @@ def test_interior_tests_on_odd_scenes(oracle, em, seed, n):
     cam = oracle.default_camera()
     cam["position"] = tuple(float(v) for v in (s["c"][:n].mean(axis=0) + np.array([0.3, 0.2, 3.0 * (np.abs(s["c"][:n]).max() + 1)])))
     f = em.check_frustum(h, cam, 320, 200)
+    assert f["bad"] == 0 and f["bad_simple"] == 0, f
+    f = em.check_frustum(h, cam, 320, 200, tile_w=32, tile_h=8)
     assert f["bad"] == 0 and f["bad_simple"] == 0, f
     em.free(h)
 
