@@ -769,6 +769,9 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
 #ifndef PKT_PREFETCH
 #define PKT_PREFETCH 0 /* L1 prefetch of the next step's nodes before a candidate phase: measured 0.3785 ms against 0.3729 ms without */
 #endif
+#ifndef PKT_QUAD
+#define PKT_QUAD true /* filter candidates per 8 x 4-pixel quadrant (8 units per macro tile) instead of per 16 x 8 sub-tile (2 units) */
+#endif
 #ifndef PKT_RAY_UNROLL
 #define PKT_RAY_UNROLL 1
 #endif
@@ -779,12 +782,28 @@ static_assert(PKT_MACRO_STACK - 32 - 3 * (SAHBVH_STACK_MAX + 2) >= 8, "PKT_MACRO
                              the warps of a block, and a block's slot is only free again when its slowest tile ends: 1 / 2 / 4
                              warps per block measured 0.362 / 0.365 / 0.374 ms on the 1 M-sphere 4K frame */
 #endif
+/* one filter unit (a sub-tile, or an 8 x 4-pixel quadrant): its frustum without the fields every unit shares (origin,
+ * pad), and its own cull bound (max over its rays of best_s; -1 = no valid ray) */
 struct PktSubFrustum {
-    SahFrustumAxis x, y, z;
-    float best_s; /* the sub-tile's cull bound (max over its rays of best_s) */
+    int mode[3];
+    float ia[3], ib[3];
+    float best_s;
 };
+__device__ __forceinline__ void pkt_sub_store(PktSubFrustum &d, const SahFrustumAxis &x, const SahFrustumAxis &y, const SahFrustumAxis &z, float best_s)
+{
+    d.mode[0] = x.mode; d.mode[1] = y.mode; d.mode[2] = z.mode;
+    d.ia[0] = x.ia; d.ia[1] = y.ia; d.ia[2] = z.ia;
+    d.ib[0] = x.ib; d.ib[1] = y.ib; d.ib[2] = z.ib;
+    d.best_s = best_s;
+}
+__device__ __forceinline__ void pkt_sub_load(const PktSubFrustum &d, const SahCamera &cam, float pad, SahFrustumAxis &x, SahFrustumAxis &y, SahFrustumAxis &z)
+{
+    x.mode = d.mode[0]; x.o = cam.px; x.ia = d.ia[0]; x.ib = d.ib[0]; x.pad = pad;
+    y.mode = d.mode[1]; y.o = cam.py; y.ia = d.ia[1]; y.ib = d.ib[1]; y.pad = pad;
+    z.mode = d.mode[2]; z.o = cam.pz; z.ia = d.ia[2]; z.ib = d.ib[2]; z.pad = pad;
+}
 
-template <bool COUNT, bool RECORDS, int S>
+template <bool COUNT, bool RECORDS, int S, bool QUAD>
 __global__ void __launch_bounds__(PKT_MACRO_WARPS1 * 32, PKT_MACRO_MIN_BLOCKS * 4 / PKT_MACRO_WARPS1)
 k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__ spheres4, SahScene sc,
                       SahCamera cam, int width, int y0, int y1, gpu_hit *__restrict__ out, float2 *__restrict__ ids,
@@ -795,11 +814,12 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
     constexpr int MW = PKT_MACRO_WARPS1;
     constexpr int TW = 16 * SX;          /* pixel columns of a macro tile */
     constexpr int MROWS = 8 * SY;        /* pixel rows of a macro tile */
+    constexpr int NF = QUAD ? 4 * S : S; /* filter units: the 8 x 4-pixel quadrants (ray slot j of every lane) or the 16 x 8 sub-tiles */
     __shared__ int32_t s_stack[MW][PKT_MACRO_STACK];
     __shared__ float s_ray[MW][S][PKT_K][3][32];   /* dx, dy, dz (d.d is recomputed: shared memory decides the occupancy) */
     __shared__ float s_bt[MW][S][PKT_K][32];
     __shared__ int32_t s_bp[MW][S][PKT_K][32];
-    __shared__ PktSubFrustum s_sub[MW][S];
+    __shared__ PktSubFrustum s_sub[MW][NF];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mtiles_x = (width + TW - 1) / TW, mtiles_y = (y1 - y0 + MROWS - 1) / MROWS;
@@ -826,6 +846,9 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
     const float pad = sqrtf(ex * ex + ey * ey + ez * ez) * 0.001953125f + sc.r_max * 0.001953125f;
     const bool geo = sc.geometric_zero_axes != 0;
     bool sub_simple_acc = true;
+    /* QUAD: lane j keeps the direction bounds of quadrant j (ray slot j of all lanes) */
+    float fminx = INFINITY, fminy = INFINITY, fminz = INFINITY, fmaxx = -INFINITY, fmaxy = -INFINITY, fmaxz = -INFINITY;
+    bool fany = false;
 #pragma unroll 1
     for (int q = 0; q < S; q++) {
         const int qx = q % SX, qy = q / SX;
@@ -841,31 +864,56 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
             s_ray[warp][q][k][0][lane] = dx; s_ray[warp][q][k][1][lane] = dy; s_ray[warp][q][k][2][lane] = dz;
             s_bt[warp][q][k][lane] = 0.0f;
             s_bp[warp][q][k][lane] = -1;
-            if (px < width && py < y1) {
+            const bool v = px < width && py < y1;
+            if (v) {
                 valid |= 1u << (q * 4 + k);
+                lmin_a = fminf(lmin_a, ra);
+            }
+            if (QUAD) {
+                /* the quadrant's bounds: one reduction per component over this ray slot of all lanes */
+                const float a0 = warp_min(v ? dx : INFINITY), a1 = warp_max(v ? dx : -INFINITY);
+                const float b0 = warp_min(v ? dy : INFINITY), b1 = warp_max(v ? dy : -INFINITY);
+                const float c0 = warp_min(v ? dz : INFINITY), c1 = warp_max(v ? dz : -INFINITY);
+                const bool any = __any_sync(full, v);
+                if (lane == q * 4 + k) { fminx = a0; fmaxx = a1; fminy = b0; fmaxy = b1; fminz = c0; fmaxz = c1; fany = any; }
+                lminx = fminf(lminx, a0); lmaxx = fmaxf(lmaxx, a1);
+                lminy = fminf(lminy, b0); lmaxy = fmaxf(lmaxy, b1);
+                lminz = fminf(lminz, c0); lmaxz = fmaxf(lmaxz, c1);
+            } else if (v) {
                 lminx = fminf(lminx, dx); lmaxx = fmaxf(lmaxx, dx);
                 lminy = fminf(lminy, dy); lmaxy = fmaxf(lmaxy, dy);
                 lminz = fminf(lminz, dz); lmaxz = fmaxf(lmaxz, dz);
-                lmin_a = fminf(lmin_a, ra);
             }
         }
-        lminx = warp_min(lminx); lminy = warp_min(lminy); lminz = warp_min(lminz);
-        lmaxx = warp_max(lmaxx); lmaxy = warp_max(lmaxy); lmaxz = warp_max(lmaxz);
         lmin_a = warp_min(lmin_a);
-        PktSubFrustum sf;
-        sah_frustum_axis_setup(sf.x, cam.px, lminx, lmaxx, pad, geo);
-        sah_frustum_axis_setup(sf.y, cam.py, lminy, lmaxy, pad, geo);
-        sah_frustum_axis_setup(sf.z, cam.pz, lminz, lmaxz, pad, geo);
-        /* an empty sub-tile (off the frame) has mode-3 axes, which accept every box: a negative bound keeps it out */
-        sf.best_s = __any_sync(full, (valid >> (q * 4)) & 15u) ? INFINITY : -1.0f;
-        if (lane == 0) s_sub[warp][q] = sf;
-        sub_simple_acc = sub_simple_acc && (sf.best_s < 0.0f || sah_frustum_simple(sf.x, sf.y, sf.z));
+        if (!QUAD) {
+            lminx = warp_min(lminx); lminy = warp_min(lminy); lminz = warp_min(lminz);
+            lmaxx = warp_max(lmaxx); lmaxy = warp_max(lmaxy); lmaxz = warp_max(lmaxz);
+            SahFrustumAxis ax, ay, az;
+            sah_frustum_axis_setup(ax, cam.px, lminx, lmaxx, pad, geo);
+            sah_frustum_axis_setup(ay, cam.py, lminy, lmaxy, pad, geo);
+            sah_frustum_axis_setup(az, cam.pz, lminz, lmaxz, pad, geo);
+            /* an empty sub-tile (off the frame) has mode-3 axes, which accept every box: a negative bound keeps it out */
+            const float bs = __any_sync(full, (valid >> (q * 4)) & 15u) ? INFINITY : -1.0f;
+            if (lane == 0) pkt_sub_store(s_sub[warp][q], ax, ay, az, bs);
+            sub_simple_acc = sub_simple_acc && (bs < 0.0f || sah_frustum_simple(ax, ay, az));
+        }
         mminx = fminf(mminx, lminx); mmaxx = fmaxf(mmaxx, lmaxx);
         mminy = fminf(mminy, lminy); mmaxy = fmaxf(mmaxy, lmaxy);
         mminz = fminf(mminz, lminz); mmaxz = fmaxf(mmaxz, lmaxz);
         mmin_a = fminf(mmin_a, lmin_a);
     }
-    const bool sub_simple = sub_simple_acc; /* warp-uniform: every (non-empty) sub-tile's frustum has the branch-free form */
+    if (QUAD) {
+        /* lane j < NF sets up quadrant j's frustum (one instance of the set-up code for all of them) */
+        SahFrustumAxis ax, ay, az;
+        sah_frustum_axis_setup(ax, cam.px, fminx, fmaxx, pad, geo);
+        sah_frustum_axis_setup(ay, cam.py, fminy, fmaxy, pad, geo);
+        sah_frustum_axis_setup(az, cam.pz, fminz, fmaxz, pad, geo);
+        const float bs = fany ? INFINITY : -1.0f;
+        if (lane < NF) pkt_sub_store(s_sub[warp][lane], ax, ay, az, bs);
+        sub_simple_acc = __all_sync(full, lane >= NF || bs < 0.0f || sah_frustum_simple(ax, ay, az));
+    }
+    const bool sub_simple = sub_simple_acc; /* warp-uniform: every (non-empty) filter unit's frustum has the branch-free form */
     /* ---- macro frustum (warp-uniform) ---- */
     SahFrustumAxis FX, FY, FZ;
     sah_frustum_axis_setup(FX, cam.px, mminx, mmaxx, pad, geo);
@@ -935,67 +983,85 @@ k_trace_primary_macro(const float *__restrict__ nodes, const float *__restrict__
             const float4 *brec = reinterpret_cast<const float4 *>(nodes + (size_t)__shfl_sync(full, nd, src) * 32 + (src & 3) * 8);
             const float4 b0 = __ldg(brec), b1 = __ldg(brec + 1);
             const float blx = b0.x, bly = b0.y, blz = b0.z, bhx = b0.w, bhy = b1.x, bhz = b1.y;
-            unsigned qmask = 1u;
-            if (S > 1) { /* compile-time: a one-tile block has nothing to filter (its frustum IS the traversal's) */
+            unsigned fm = 1u;
+            if (NF > 1) { /* compile-time: a one-tile block has nothing to filter (its frustum IS the traversal's) */
                 bool sub_pass = false;
-                if (lane < S) {
-                    const PktSubFrustum &sf = s_sub[warp][lane];
+                if (lane < NF) {
+                    SahFrustumAxis ax, ay, az;
+                    pkt_sub_load(s_sub[warp][lane], cam, pad, ax, ay, az);
+                    const float bs = s_sub[warp][lane].best_s;
                     float tq;
-                    sub_pass = sub_simple ? sah_frustum_box_simple(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq)
-                                          : sah_frustum_box(sf.x, sf.y, sf.z, blx, bly, blz, bhx, bhy, bhz, sf.best_s, tq);
+                    sub_pass = sub_simple ? sah_frustum_box_simple(ax, ay, az, blx, bly, blz, bhx, bhy, bhz, bs, tq)
+                                          : sah_frustum_box(ax, ay, az, blx, bly, blz, bhx, bhy, bhz, bs, tq);
                 }
-                qmask = __ballot_sync(full, sub_pass) & ((1u << S) - 1u);
+                fm = __ballot_sync(full, sub_pass) & ((1u << NF) - 1u);
             }
-            while (qmask) {
-                const int q = __ffs(qmask) - 1;
-                qmask &= qmask - 1;
-                /* the reference's sphere test and, for a would-be winner, its own leaf-box test, ray by ray (the box is
-                 * already here for the filter, so there is no reason to batch the box tests as K2p does) */
-                bool changed = false;
-                const float *rq = &s_ray[warp][q][0][0][lane];   /* ray k: rq[k*96], rq[k*96+32], rq[k*96+64] */
-                float *btq = &s_bt[warp][q][0][lane];            /* ray k: btq[k*32] */
-                int32_t *bpq = &s_bp[warp][q][0][lane];
-                unsigned vq = (valid >> (q * 4)) & 15u;
+            /* the lane's rays to test: every ray slot of a passing sub-tile, or the slots of the passing quadrants */
+            unsigned vq = valid;
+            if (QUAD) {
+                vq &= fm;
+            } else {
+                unsigned em = 0;
+#pragma unroll
+                for (int q = 0; q < S; q++) em |= ((fm >> q) & 1u) ? (15u << (q * 4)) : 0u;
+                vq &= em;
+            }
+            /* the reference's sphere test and, for a would-be winner, its own leaf-box test, ray by ray (the box is
+             * already here for the filter, so there is no reason to batch the box tests as K2p does) */
+            unsigned chg = 0;
+            const float *rq = &s_ray[warp][0][0][0][lane];   /* ray slot j: rq[j*96], rq[j*96+32], rq[j*96+64] */
+            float *btq = &s_bt[warp][0][0][lane];            /* ray slot j: btq[j*32] */
+            int32_t *bpq = &s_bp[warp][0][0][lane];
 #pragma unroll kPktRayUnroll
-                for (; vq; vq &= vq - 1u, rq += 0) {
-                    const int k = __ffs(vq) - 1;
-                    SahRay r;
-                    r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
-                    r.dx = rq[k * 96]; r.dy = rq[k * 96 + 32]; r.dz = rq[k * 96 + 64];
-                    r.a = F_ADD(F_ADD(F_MUL(r.dx, r.dx), F_MUL(r.dy, r.dy)), F_MUL(r.dz, r.dz));
-                    if (COUNT) cnt.spheres++;
-                    float t;
-                    if (sah_sphere_t(r, s.x, s.y, s.z, s.w, t)) {
-                        const float bt = btq[k * 32];
-                        const int32_t bp = bpq[k * 32];
-                        if (bp < 0 || t < bt || (t == bt && sidx > bp)) {
-                            if (COUNT) cnt.exact++;
-                            if (sah_box_exact_fast(r, blx, bly, blz, bhx, bhy, bhz)) {
-                                btq[k * 32] = t;
-                                bpq[k * 32] = sidx;
-                                changed = true;
-                            }
+            for (; vq; vq &= vq - 1u) {
+                const int jr = __ffs(vq) - 1;
+                SahRay r;
+                r.ox = cam.px; r.oy = cam.py; r.oz = cam.pz;
+                r.dx = rq[jr * 96]; r.dy = rq[jr * 96 + 32]; r.dz = rq[jr * 96 + 64];
+                r.a = F_ADD(F_ADD(F_MUL(r.dx, r.dx), F_MUL(r.dy, r.dy)), F_MUL(r.dz, r.dz));
+                if (COUNT) cnt.spheres++;
+                float t;
+                if (sah_sphere_t(r, s.x, s.y, s.z, s.w, t)) {
+                    const float bt = btq[jr * 32];
+                    const int32_t bp = bpq[jr * 32];
+                    if (bp < 0 || t < bt || (t == bt && sidx > bp)) {
+                        if (COUNT) cnt.exact++;
+                        if (sah_box_exact_fast(r, blx, bly, blz, bhx, bhy, bhz)) {
+                            btq[jr * 32] = t;
+                            bpq[jr * 32] = sidx;
+                            chg |= 1u << jr;
                         }
                     }
                 }
-                if (__any_sync(full, changed)) {
-                    float w = 0.0f; /* worst (largest) cull bound over this lane's valid rays of sub-tile q */
+            }
+            /* new cull bounds of the filter units that changed */
+            unsigned cm = __reduce_or_sync(full, chg);
+            if (!QUAD) { /* ray slots -> sub-tiles */
+                unsigned um = 0;
+#pragma unroll
+                for (int q = 0; q < S; q++) um |= ((cm >> (q * 4)) & 15u) ? (1u << q) : 0u;
+                cm = um;
+            }
+            while (cm) {
+                const int un = __ffs(cm) - 1;
+                cm &= cm - 1;
+                float w = 0.0f; /* worst (largest) cull bound over this lane's valid rays of the unit */
+                if (QUAD) {
+                    if ((valid >> un) & 1u) w = bpq[un * 32] >= 0 ? F_FMA(btq[un * 32], SAH_REL_CULL, cull_abs) : INFINITY;
+                } else {
 #pragma unroll
                     for (int k = 0; k < PKT_K; k++)
-                        if (valid & (1u << (q * 4 + k)))
-                            w = fmaxf(w, s_bp[warp][q][k][lane] >= 0 ? F_FMA(s_bt[warp][q][k][lane], SAH_REL_CULL, cull_abs) : INFINITY);
-                    w = warp_max_nonneg(w);
-                    if (lane == 0) s_sub[warp][q].best_s = w;
-                    any_changed = true;
+                        if (valid & (1u << (un * 4 + k)))
+                            w = fmaxf(w, bpq[(un * 4 + k) * 32] >= 0 ? F_FMA(btq[(un * 4 + k) * 32], SAH_REL_CULL, cull_abs) : INFINITY);
                 }
+                w = warp_max_nonneg(w);
+                if (lane == 0) s_sub[warp][un].best_s = w;
+                any_changed = true;
             }
             __syncwarp(); /* the next candidate's filter reads the bounds just written */
         }
-        if (any_changed) { /* warp-uniform */
-            float w = 0.0f;
-#pragma unroll
-            for (int q = 0; q < S; q++) w = fmaxf(w, s_sub[warp][q].best_s);
-            pkt_best_s = w;
+        if (any_changed) { /* warp-uniform: the traversal's bound is the largest unit bound (an empty unit's -1 counts as 0) */
+            pkt_best_s = warp_max_nonneg(lane < NF ? fmaxf(s_sub[warp][lane].best_s, 0.0f) : 0.0f);
         }
     }
     /* ---- results: the warp's own rows (32 pixels = one 128-byte id row per store; a 16-pixel tile stores two rows) ---- */
@@ -1730,13 +1796,13 @@ int sahbvh_launch_primary(gpu_bvh *b, const Camera *cam, int width, int height, 
             const int mw = PKT_MACRO_WARPS1;
             const unsigned mgrid = (unsigned)((mtiles + mw - 1) / mw);
             if (count)
-                k_trace_primary_macro<true, true, 2><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                k_trace_primary_macro<true, true, 2, PKT_QUAD><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                out, ids, ids_mode, dfs_from, b->d_counters);
             else if (out)
-                k_trace_primary_macro<false, true, 2><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                k_trace_primary_macro<false, true, 2, PKT_QUAD><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                 out, ids, ids_mode, dfs_from, nullptr);
             else
-                k_trace_primary_macro<false, false, 2><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
+                k_trace_primary_macro<false, false, 2, PKT_QUAD><<<mgrid, mw * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,
                                                                                  nullptr, ids, ids_mode, dfs_from, nullptr);
         } else if (count)
             k_trace_primary_packet<true, true><<<grid, PKT_WARPS * 32, 0, st>>>(b->d_wide_full, b->d_spheres4, sc, c, width, y0, y1,

@@ -125,6 +125,17 @@ class HostEmul:
         assert rc == 0
         return dict(zip(("pairs", "accepted", "bad", "bad_simple"), map(int, out)))
 
+    def trace_primary_packet(self, h, cam, w, hgt, tile_w=16, tile_h=8, sub_w=0, sub_h=0, y0=0, y1=None):
+        """host restatement of the packet kernels' algorithm: tile_w x tile_h tiles culled by their frustum; with
+        sub_w, sub_h > 0 the macro-tile variant (candidates filtered by sub-tile frusta with their own cull bounds)"""
+        y1 = hgt if y1 is None else y1
+        hits = np.zeros((y1 - y0) * w, HIT_DT)
+        st = (C.c_uint64 * 7)()
+        self.lib.emul_trace_primary_packet(C.c_void_p(h), _ptr(cam), C.c_int(w), C.c_int(hgt), C.c_int(y0), C.c_int(y1),
+                                           C.c_int(tile_w), C.c_int(tile_h), C.c_int(sub_w), C.c_int(sub_h), _ptr(hits), st)
+        stats = dict(zip(("rays", "inner_visits", "sphere_tests", "exact_box_tests", "hits", "max_stack", "max_visits"), map(int, st)))
+        return hits, stats
+
     def primary_rays(self, cam, w, h, y0=0, y1=None):
         y1 = h if y1 is None else y1
         out = np.zeros((y1 - y0) * w, RAY_DT)

@@ -159,9 +159,13 @@ static SahScene scene_of(const emul_bvh *e)
     return sc;
 }
 
+/* sub_w, sub_h > 0: the MACRO-tile variant (k_trace_primary_macro): the tile_w x tile_h tile is traversed once with
+ * its own frustum, and a candidate leaf is tested only by the rays of the sub_w x sub_h sub-tiles whose own frustum
+ * (with the sub-tile's own cull bound) its box passes. */
 extern "C" void emul_trace_primary_packet(const emul_bvh *e, const Camera *cam, int width, int height, int y0, int y1,
-                                          int tile_w, int tile_h, gpu_hit *out, gpu_trace_stats *stats)
+                                          int tile_w, int tile_h, int sub_w, int sub_h, gpu_hit *out, gpu_trace_stats *stats)
 {
+    struct Sub { SahFrustumAxis x, y, z; float best_s; std::vector<int> rays; };
     SahCamera c;
     fill_camera(cam, width, height, &c);
     const SahScene sc = scene_of(e);
@@ -194,6 +198,26 @@ extern "C" void emul_trace_primary_packet(const emul_bvh *e, const Camera *cam, 
             float min_len = sqrtf(min_a);
             const float cull_abs = (min_len > 0.0f) ? (2.0f * sc.r_max) / min_len : INFINITY;
             float pkt_best_s = INFINITY;
+            std::vector<Sub> subs;
+            if (sub_w > 0 && sub_h > 0)
+                for (int sy = 0; sy < ny; sy += sub_h)
+                    for (int sx = 0; sx < nx; sx += sub_w) {
+                        Sub sb;
+                        float smn[3] = {INFINITY, INFINITY, INFINITY}, smx[3] = {-INFINITY, -INFINITY, -INFINITY};
+                        for (int yy = sy; yy < std::min(sy + sub_h, ny); yy++)
+                            for (int xx = sx; xx < std::min(sx + sub_w, nx); xx++) {
+                                const int i = yy * nx + xx;
+                                sb.rays.push_back(i);
+                                smn[0] = fminf(smn[0], dx[i]); smx[0] = fmaxf(smx[0], dx[i]);
+                                smn[1] = fminf(smn[1], dy[i]); smx[1] = fmaxf(smx[1], dy[i]);
+                                smn[2] = fminf(smn[2], dz[i]); smx[2] = fmaxf(smx[2], dz[i]);
+                            }
+                        sah_frustum_axis_setup(sb.x, c.px, smn[0], smx[0], pad, geo);
+                        sah_frustum_axis_setup(sb.y, c.py, smn[1], smx[1], pad, geo);
+                        sah_frustum_axis_setup(sb.z, c.pz, smn[2], smx[2], pad, geo);
+                        sb.best_s = INFINITY;
+                        subs.push_back(sb);
+                    }
             stack.clear();
             stack.push_back(0);
             while (!stack.empty()) {
@@ -215,7 +239,14 @@ extern "C" void emul_trace_primary_packet(const emul_bvh *e, const Camera *cam, 
                     int32_t sidx = ~ref[ch];
                     if ((uint32_t)sidx >= (uint32_t)sc.n_spheres) continue;
                     const float *s = spheres4 + (size_t)sidx * 4, *q = w + ch * 8;
+                    std::vector<char> take(nr, subs.empty() ? 1 : 0);
+                    for (Sub &sb : subs) {
+                        float tq;
+                        if (sah_frustum_box(sb.x, sb.y, sb.z, q[0], q[1], q[2], q[3], q[4], q[5], sb.best_s, tq))
+                            for (int i : sb.rays) take[i] = 1;
+                    }
                     for (int i = 0; i < nr; i++) {
+                        if (!take[i]) continue;
                         SahRay r;
                         r.ox = c.px; r.oy = c.py; r.oz = c.pz;
                         r.dx = dx[i]; r.dy = dy[i]; r.dz = dz[i];
@@ -236,6 +267,11 @@ extern "C" void emul_trace_primary_packet(const emul_bvh *e, const Camera *cam, 
                     for (int i = 0; i < nr; i++)
                         wmax = fmaxf(wmax, bp[i] >= 0 ? F_FMA(bt[i], SAH_REL_CULL, cull_abs) : INFINITY);
                     pkt_best_s = wmax;
+                    for (Sub &sb : subs) {
+                        float wq = 0.0f;
+                        for (int i : sb.rays) wq = fmaxf(wq, bp[i] >= 0 ? F_FMA(bt[i], SAH_REL_CULL, cull_abs) : INFINITY);
+                        sb.best_s = wq;
+                    }
                 }
                 bool pl = pass[0] && ref[0] >= 0, pr = pass[1] && ref[1] >= 0;
                 if (pl && pr) {
