@@ -761,7 +761,7 @@ def run_b200(args):
         "hbm_compulsory_frac": compulsory_bytes / k_s / 1e9 / hbm_peak, "hbm_compulsory_bytes_per_launch": compulsory_bytes,
         "l2_touched_frac": touched_bytes / k_s / 1e9 / peaks["l2_read_gbs"] if peaks["l2_read_gbs"] else None,
         "l2_touched_bytes_per_launch": touched_bytes, "l2_read_peak_gbs": peaks["l2_read_gbs"],
-        "tile_work": {"tile": "32x8-pixel macro tile (two 16x8 sub-tiles)" if kernel_id == 2 else "16x8-pixel tile",
+        "tile_work": {"tile": "32x8-pixel macro tile (candidates filtered per 8x4-pixel quadrant)" if kernel_id == 2 else "16x8-pixel tile",
                       "tiles": tiles, "nodes_popped_per_tile": stats["inner_visits"] / tiles,
                       "sphere_tests_per_ray": stats["sphere_tests"] / n_local,
                       "exact_leaf_box_tests_per_ray": stats["exact_box_tests"] / n_local, "max_stack": stats["max_stack"]},
