@@ -196,7 +196,8 @@ int sahbvh_host_unpin(void *ptr);
 #define SAHBVH_PRIMARY_PER_RAY 0
 #define SAHBVH_PRIMARY_PACKET 1
 /*   SAHBVH_PRIMARY_MACRO   one warp per 32x8 pixel macro tile: interior culling once per 256 rays, a candidate leaf is
- *                          first tested against the two 16x8 sub-tile frusta and only their rays run the exact tests
+ *                          first tested against the frusta of the tile's eight 8x4-pixel quadrants (one lane each) and
+ *                          only the rays of the quadrants it can touch run the exact tests
  *   SAHBVH_PRIMARY_AUTO    (default) PACKET or MACRO, whichever the first launches on this handle and frame shape
  *                          measure as faster (event pairs around the launches, queried later; nothing synchronises) */
 #define SAHBVH_PRIMARY_MACRO 2

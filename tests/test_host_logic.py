@@ -420,3 +420,38 @@ def test_bench_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "rays per step" in cb["sample"]
     assert "workload" in d["config"] and "20000" in d["config"]["workload"]
+
+
+@pytest.mark.parametrize("kind,n", [("benchmark", 20000), ("default", 20), ("odd", 700)])
+def test_packet_and_macro_tile_algorithm_on_the_host(oracle, kind, n):
+    """The packet kernels' algorithm restated on the host (tests/host_emul, emul_trace_primary_packet over the same
+    traverse_core.cuh arithmetic): tiles culled once by their frustum (K2p: 16x8), and the macro-tile variant (K2m:
+    32x8 tiles, a candidate leaf tested only by the rays of the sub-tiles / quadrants whose own frustum and cull bound it
+    passes) give the oracle's records for every tiling, and the filter removes sphere tests without adding node visits."""
+    from common import HostEmul
+    em = HostEmul("binary")
+    if kind == "benchmark":
+        oracle.srand(1)
+        s = oracle.scene_benchmark(n)
+    elif kind == "default":
+        oracle.srand(7)
+        s = oracle.scene_random(n)
+    else:
+        from test_fuzz import odd_scene
+        s = odd_scene(np.random.default_rng(3), n)
+    nodes = oracle.build(s, 0, n, 0)
+    h = em.build(s.copy(), n, 0, n, 0)
+    cam = oracle.default_camera()
+    if kind == "odd":
+        cam["position"] = tuple(float(v) for v in (s["c"][:n].mean(axis=0) + np.array([0.3, 0.2, 3.0 * (np.abs(s["c"][:n]).max() + 1)])))
+    W, H = 333, 203                                   # ragged: partial tiles on the right and at the bottom
+    want, _ = oracle.trace_bvh(nodes, s, n, oracle.primary_rays(cam, W, H))
+    stats = {}
+    for tiling in ((16, 8, 0, 0), (32, 8, 16, 8), (32, 8, 8, 4), (32, 16, 8, 4), (33, 7, 5, 3)):
+        got, st = em.trace_primary_packet(h, cam, W, H, *tiling)
+        assert_hits_equal(got, want, f"{kind}: tiling {tiling}")
+        stats[tiling] = st
+    assert stats[(32, 8, 8, 4)]["inner_visits"] == stats[(32, 8, 16, 8)]["inner_visits"]        # the filter never changes the traversal ...
+    assert stats[(32, 8, 8, 4)]["sphere_tests"] <= stats[(32, 8, 16, 8)]["sphere_tests"]        # ... it only removes sphere tests
+    assert stats[(32, 8, 16, 8)]["inner_visits"] < stats[(16, 8, 0, 0)]["inner_visits"] or kind == "default"
+    em.free(h)
