@@ -7,8 +7,10 @@
 * handles without the 64-byte binary tree (the default);
 * one process, N devices (gpu_bvh_set) -- sharded frames and ray buffers equal the single-device result;
 * reference-generated goldens for the 10 M-sphere scene (tests/golden/make_golden_10m.py);
-* the 1 M-sphere 4K frame the bench times: packet == per-ray == ray-buffer over the FULL frame, and a
-  200 K-pixel sample against the oracle.
+* the 1 M-sphere 4K frame the bench times: packet == macro-tile == per-ray == ray-buffer over the FULL frame, and a
+  200 K-pixel sample against the oracle;
+* the macro-tile kernel (SAHBVH_PRIMARY_MACRO) wherever the packet kernel is checked, SAHBVH_PRIMARY_AUTO's sampling
+  and settling, random cameras with odd frame sizes, the persisting-L2 window option, the id-count reduction.
 """
 import ctypes as C
 import json
