@@ -751,17 +751,19 @@ k_trace_primary_packet(const float *__restrict__ nodes, const float *__restrict_
 }
 
 /*
- * K2m: packet traversal over MACRO tiles.  One warp owns 32 x (8 SUBY) pixels = S = 2 SUBY sub-tiles of 16 x 8 (the
- * tile of K2p), i.e. 4 S rays per lane.  The interior culling -- half of K2p's instructions -- runs ONCE per macro
- * tile against the macro frustum; a candidate leaf is then tested against the S sub-tile frusta (one lane per
- * sub-tile, one ballot) and only the sub-tiles it can touch run the reference's sphere / leaf-box tests, with their
- * own cull bound.  Per ray the exact tests are the same as in K2p (best over leaves whose own tests pass), so the
- * records are identical; what is shared wider is only the conservative culling.
+ * K2m: packet traversal over MACRO tiles.  One warp (= one block) owns 32 x 8 pixels = S = 2 of K2p's 16 x 8 tiles side
+ * by side, i.e. 8 rays per lane (the template also takes S = 1 and S = 4; 2 ships).  The interior culling -- half of
+ * K2p's instructions -- runs ONCE per macro tile against the macro frustum.  A candidate leaf is then tested against the
+ * frusta of the tile's FILTER UNITS -- the eight 8 x 4-pixel quadrants (QUAD: quadrant j is ray slot j of all 32 lanes;
+ * lane j owns its frustum and tests it, one ballot), or the S sub-tiles -- each with its own cull bound, and a lane runs
+ * the reference's sphere / leaf-box tests only for its ray slots whose unit passed: 2.3 sphere tests per ray on the
+ * headline frame instead of K2p's 5.2.  Per ray the exact tests are the same as in K2p (best over leaves whose own tests
+ * pass), so the records are identical; what is shared wider, and filtered finer, is only the conservative culling.
  * A macro tile is 32 pixels wide, so the warp's own rows are whole 128-byte id rows (1 KiB of records): results
  * leave through the warp's shared-memory state without a block barrier.
  */
 #ifndef PKT_MACRO_MIN_BLOCKS
-#define PKT_MACRO_MIN_BLOCKS 8 /* x 4 warps: 64 registers and 6.1 KB of shared memory per warp = 32 warps per SM */
+#define PKT_MACRO_MIN_BLOCKS 8 /* x 4 / PKT_MACRO_WARPS1 blocks: 64 registers and 6.3 KB of shared memory per warp = 31 warps per SM */
 #endif
 #ifndef PKT_MACRO_STACK
 #define PKT_MACRO_STACK 256
